@@ -1,0 +1,49 @@
+"""Direct oracle <-> live reference comparison on fresh seeds.  Runs only where the reference
+checkout exists (the build container); the committed golden fixtures cover everywhere else."""
+import numpy as np
+import pytest
+
+from neuralnetworklibrary_b200 import testing as syn
+from oracle import oracle as orc
+from tests import ref_runner as ref
+from tests.test_oracle_golden import assert_rel
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="reference checkout not present")
+
+
+@pytest.mark.parametrize("H,W", [(64, 64), (100, 167), (512, 512)])
+def test_anchors(H, W):
+    assert np.array_equal(ref.anchors(H, W).view(np.uint32), orc.anchors(H, W).view(np.uint32))
+
+
+@pytest.mark.parametrize("seed,H,W,C,B,M", [(11, 128, 128, 20, 2, 5), (12, 96, 160, 8, 3, 12), (13, 256, 256, 80, 2, 20)])
+def test_loss(seed, H, W, C, B, M):
+    an = orc.anchors(H, W)
+    gb, gc = syn.make_targets(B, M, H, W, C, seed=seed, min_side=12.0, max_frac=0.6)
+    clas, reg = syn.make_train_activations(B, an.shape[0], C, seed=seed, edge_cases=64)
+    r = ref.loss(an, clas, reg, gb, gc)
+    o = orc.loss(an, clas.numpy(), reg.numpy(), gb.numpy(), gc.numpy(), want_matches=True)
+    np.testing.assert_allclose(o["out3"], r["out3"], rtol=1e-5, atol=0)
+    assert_rel(o["dclas"], r["dclas"])
+    assert_rel(o["dreg"], r["dreg"])
+    for i in range(B):
+        v = gc[i] >= 0
+        pos, neg, m = ref.assign(an, gb[i][v], gc[i][v])
+        assert np.array_equal(np.where(o["matches"][i] >= 0, o["matches"][i], -1), m)
+        assert np.array_equal(np.nonzero(o["matches"][i] == -1)[0], neg)
+
+
+@pytest.mark.parametrize("seed,mu", [(21, -6.0), (22, -3.5)])
+def test_postproc(seed, mu):
+    H, W, C, B = 128, 192, 20, 2
+    an = orc.anchors(H, W)
+    clas, reg = syn.make_infer_activations(B, an.shape[0], C, seed=seed, anchors=an, mu=mu, clusters=5)
+    rb, rc, rs = ref.postproc(clas, reg, an, H, W)
+    o = orc.postproc(clas.numpy(), reg.numpy(), an, H, W)
+    for i in range(B):
+        n = int(o["counts"][i])
+        assert n == len(rb[i])
+        if n:
+            assert np.array_equal(np.array(rc[i]), o["classes"][i, :n])
+            assert np.array_equal(np.array(rs[i]), o["scores"][i, :n])
+            np.testing.assert_allclose(o["boxes"][i, :n], np.stack(rb[i]), rtol=1e-5, atol=0)
