@@ -1,0 +1,132 @@
+/*
+ * retina_b200.h -- C ABI of libretina_sm100.so: the B200-native (sm_100a) implementation of the
+ * RetinaNet loss / post-processing hot path of NickTravers/NeuralNetworkLibrary.
+ *
+ * The reference has no FFI layer: its boundary is Python duck typing at four call sites (SURVEY.md
+ * section 8b).  The entry points below are what a binding for that boundary calls; each one names
+ * the reference code it replaces (file:line under the reference checkout).  INTEGRATION.md shows the
+ * ctypes stubs; neuralnetworklibrary_b200/_lib.py is the binding used by the drop-in wrappers.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless marked "host";
+ *   - the caller owns every buffer (the wrappers let torch's caching allocator provide them);
+ *   - no hidden allocation, no device synchronisation, no default-stream use: every launch goes to
+ *     the `stream` argument (a cudaStream_t passed as void*), so calls are CUDA-graph capturable and
+ *     re-entrant per stream as long as each stream has its own workspace;
+ *   - return value: RN_OK or an RN_ERR_* code; rn_last_error() gives the message (thread local);
+ *   - there is no CPU fallback.  Without a CUDA device every compute entry returns RN_ERR_CUDA.
+ *
+ * Anchors.  Anchor a lives at level l (P3..P7), grid cell (iy, ix) and slot k of the K = nr*ns base
+ * boxes, a = off_l + (iy*gw_l + ix)*K + k (reference retinanet.py:467-469, :491-495).  Kernels take
+ * EITHER a device table `anchors` [A,4] fp32 (any anchor set, e.g. the reference's own tensor) OR
+ * anchors == NULL plus the image size (H, W) and the host table `base` [5][K][4] float64 =
+ * size_l * get_anchor_set() (retinanet.py:439-451, :480, :492) and generate the anchor on the fly as
+ * float32(base + shift) -- the reference's float64 arithmetic followed by TEN()'s rounding
+ * (General/Core.py:61-62), bit for bit.
+ *
+ * matches encoding: >= 0 index of the matched ground-truth box (among the image's non-padding
+ * rows, in order), RN_MATCH_NEG background, RN_MATCH_IGNORE max IoU in [neg_thr, pos_thr].
+ */
+#ifndef RETINA_B200_H
+#define RETINA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RN_OK 0
+#define RN_ERR_INVALID_ARG 1 /* bad shape / null pointer / unsupported parameter value */
+#define RN_ERR_WORKSPACE 2   /* workspace too small or misaligned */
+#define RN_ERR_CUDA 3        /* CUDA runtime error (message carries cudaGetErrorString) */
+
+#define RN_MATCH_NEG (-1)
+#define RN_MATCH_IGNORE (-2)
+
+#define RN_NUM_LEVELS 5 /* P3..P7, retinanet.py:478 */
+#define RN_MAX_K 16     /* max base boxes per cell (the reference uses 9) */
+#define RN_MAX_TOP_K 4096
+
+/* Message of the last error on the calling thread ("" if none). */
+const char *rn_last_error(void);
+/* ABI version (bumped on any signature change). */
+int rn_abi_version(void);
+
+/* A = K * sum_l ceil(H/2^l)*ceil(W/2^l), l = 3..7 (retinanet.py:488).  Host-only arithmetic. */
+int rn_num_anchors(int H, int W, int K);
+
+/* AnchorGenerator.__call__ (retinanet.py:485-495): writes the [A,4] fp32 anchor table. */
+int rn_anchors(int H, int W, const double *base /*host [5][K][4]*/, int K, float *anchors_out /*[A,4]*/,
+               void *stream);
+
+/* jaccard + match_anchors_objects for a whole batch (Vision.py:234-256, :1474-1511, and the padding
+ * strip of Vision.py:1637-1638: a ground-truth row is padding iff gt_cats < 0).
+ *   gt_boxes [B,M,4] fp32, gt_cats [B,M] int64 -> matches [B,A] int32, npos [B] int32 (#positives).
+ * max_iou ([B,A] fp32) may be NULL. */
+int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, int M, int H, int W,
+              const double *base /*host*/, int K, const float *anchors /*[A,4] or NULL*/, int A,
+              float pos_thr, float neg_thr, int32_t *matches, int32_t *npos, float *max_iou, void *stream);
+
+/* ComputeMaxOverlaps (Vision.py:1666-1694): per ground-truth row the max IoU with any anchor.
+ *   out [B,M] fp32; padding rows receive -1. */
+int rn_max_overlaps(const float *gt_boxes, const int64_t *gt_cats, int B, int M, int H, int W,
+                    const double *base /*host*/, int K, const float *anchors /*or NULL*/, int A,
+                    float *out, void *stream);
+
+/* Workspace for rn_loss (bytes; 256-byte aligned base required). */
+size_t rn_loss_workspace_bytes(int B, int A, int C);
+
+/* ssd1 + focal_loss_retina + smoothL1_loss_retina + SSD_loss.__call__ forward AND backward in one
+ * streaming pass (Vision.py:1513-1644), given the assignment from rn_assign.
+ *   clas [B,A,C] fp32 probabilities (post-sigmoid, as the reference's heads return them), reg [B,A,4].
+ *   out3 [3] fp32 = {loss, reg_loss, clas_loss}: the value SSD_loss returns and the two attributes it
+ *     stores (Vision.py:1643-1644).  B_global >= B is the batch size the sums are divided by (an image
+ *     shard passes the global batch; the three outputs are then this shard's additive share).
+ *   dclas [B,A,C], dreg [B,A,4]: d loss / d clas and d loss / d reg for upstream gradient 1, fully
+ *     written (zeros where the reference's gradient is zero).  Pass both NULL for a forward-only call
+ *     (the reference's `evaluate` under no_grad). */
+int rn_loss(const float *clas, const float *reg, const float *gt_boxes, const int64_t *gt_cats,
+            const int32_t *matches, const int32_t *npos, int B, int A, int C, int M, int H, int W,
+            const double *base /*host*/, int K, const float *anchors /*or NULL*/, double alpha,
+            double gamma, double beta, int B_global, float *dclas, float *dreg, float *out3,
+            void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward with a non-unit upstream gradient: scales dclas[n_clas], dreg[n_reg] in place by the
+ * DEVICE scalar *grad_out; the kernel exits immediately when *grad_out == 1 (what loss.backward()
+ * passes, General/Learner.py:514), so the common case costs one empty launch and no host sync. */
+int rn_scale_grads(float *dclas, size_t n_clas, float *dreg, size_t n_reg, const float *grad_out,
+                   void *stream);
+
+/* Workspace for rn_postproc (bytes). */
+size_t rn_postproc_workspace_bytes(int B, int A, int top_k);
+
+/* BBoxPredictor.__call__ + nms with rel_thresh/inc/dup = None (retinanet.py:732-812, :523-711):
+ * class max + threshold + decode + clip + empty-box filter, top_k by score, class-aware greedy NMS
+ * (bitmask form), first max_keep survivors.
+ *   mean, std: host [4].  max_keep <= top_k <= RN_MAX_TOP_K.
+ *   outputs [B,max_keep,...] score-descending; counts [B]; anchor_idx [B,max_keep] (the keep indices
+ *   the reference only has implicitly) and n_candidates [B] (#boxes handed to nms) may be NULL.
+ *   Ties in score are ordered by ascending anchor index (the reference's sort is unstable). */
+int rn_postproc(const float *clas, const float *reg, int B, int A, int C, int H, int W,
+                const double *base /*host*/, int K, const float *anchors /*or NULL*/,
+                const float *mean /*host*/, const float *std /*host*/, float thresh, float max_overlap,
+                int top_k, int max_keep, float *boxes, int64_t *classes, float *scores,
+                int32_t *anchor_idx, int32_t *counts, int32_t *n_candidates, void *workspace,
+                size_t workspace_bytes, void *stream);
+
+/* Workspace for rn_nms (bytes). */
+size_t rn_nms_workspace_bytes(int n, int top_k);
+
+/* nms() on caller-provided boxes (retinanet.py:523-711 with rel_thresh/inc/dup = None; the TTA call
+ * site Vision.py:2118).  boxes [n,4] fp32, classes [n] int64, scores [n] fp32.
+ *   keep_idx [max_keep] int32: indices into the inputs, score-descending; count [1] int32. */
+int rn_nms(const float *boxes, const int64_t *classes, const float *scores, int n, float max_overlap,
+           int top_k, int max_keep, int32_t *keep_idx, int32_t *count, void *workspace,
+           size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

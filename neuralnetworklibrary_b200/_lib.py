@@ -1,0 +1,158 @@
+"""ctypes binding of libretina_sm100.so (C ABI: include/retina_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `build_library()` with nvcc for sm_100a.
+There is NO fallback: if the shared object is missing or a tensor is not on a CUDA device, the
+wrappers raise.
+"""
+import ctypes as C
+import glob
+import os
+import subprocess
+import threading
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libretina_sm100.so")
+SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_post.cu"]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-fmad=false",  # never contract a*b+c behind our back; fused ops are spelled fmaf() explicitly
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+RN_OK, RN_ERR_INVALID_ARG, RN_ERR_WORKSPACE, RN_ERR_CUDA = 0, 1, 2, 3
+MATCH_NEG, MATCH_IGNORE = -1, -2
+MAX_TOP_K = 4096
+MAX_K = 16
+
+
+class RetinaB200Error(RuntimeError):
+    pass
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_PKG, "csrc", s) for s in SOURCES] + glob.glob(os.path.join(_PKG, "csrc", "*.cuh")) + \
+        [os.path.join(_ROOT, "include", "retina_b200.h")]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force=False, verbose=False):
+    """Compiles every CUDA source of the package for sm_100a into LIB_PATH (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", LIB_PATH] + [os.path.join(_PKG, "csrc", s) for s in SOURCES]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RetinaB200Error("nvcc failed:\n" + res.stdout)
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+_vp, _f32p, _f64p, _i32p, _i64p = C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p
+_hf32p = C.POINTER(C.c_float)
+
+# name -> (restype, argtypes).  Mirrors include/retina_b200.h one to one (tests check the symbols).
+PROTOTYPES = {
+    "rn_last_error": (C.c_char_p, []),
+    "rn_abi_version": (C.c_int, []),
+    "rn_num_anchors": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "rn_anchors": (C.c_int, [C.c_int, C.c_int, _f64p, C.c_int, _f32p, _vp]),
+    "rn_assign": (C.c_int, [_f32p, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _f32p, C.c_int,
+                            C.c_float, C.c_float, _i32p, _i32p, _f32p, _vp]),
+    "rn_max_overlaps": (C.c_int, [_f32p, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _f32p, C.c_int,
+                                  _f32p, _vp]),
+    "rn_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "rn_loss": (C.c_int, [_f32p, _f32p, _f32p, _i64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                          C.c_int, _f64p, C.c_int, _f32p, C.c_double, C.c_double, C.c_double, C.c_int,
+                          _f32p, _f32p, _f32p, _vp, C.c_size_t, _vp]),
+    "rn_scale_grads": (C.c_int, [_f32p, C.c_size_t, _f32p, C.c_size_t, _f32p, _vp]),
+    "rn_postproc_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "rn_postproc": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _f32p,
+                              _hf32p, _hf32p, C.c_float, C.c_float, C.c_int, C.c_int, _f32p, _i64p, _f32p,
+                              _i32p, _i32p, _i32p, _vp, C.c_size_t, _vp]),
+    "rn_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "rn_nms": (C.c_int, [_f32p, _i64p, _f32p, C.c_int, C.c_float, C.c_int, C.c_int, _i32p, _i32p, _vp,
+                         C.c_size_t, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """Loads the shared library (never builds implicitly on a GPU box: a missing .so is an error)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RetinaB200Error(
+                    "%s not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
+            L = C.CDLL(LIB_PATH)
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != RN_OK:
+        msg = load().rn_last_error().decode("utf-8", "replace")
+        if rc == RN_ERR_INVALID_ARG:
+            raise ValueError(msg)  # the reference reports bad arguments as ValueError (Learner.py:339-340)
+        raise RetinaB200Error("libretina_sm100 error %d: %s" % (rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RetinaB200Error("%s must live on a CUDA device: this path has no CPU fallback" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+def base_ptr(base_np):
+    """Host pointer to the float64 [5][K][4] base table (a contiguous numpy array)."""
+    return base_np.ctypes.data_as(_f64p)
+
+
+class Workspace(object):
+    """Grow-only per-(device, stream) scratch buffer handed to the library (256-byte aligned by the
+    caching allocator)."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, nbytes, device):
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf

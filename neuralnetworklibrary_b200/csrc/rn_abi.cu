@@ -1,0 +1,68 @@
+// rn_abi.cu -- error state, geometry and the small host-only entry points of libretina_sm100.so.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "rn_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+int rn_set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int rn_check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();  // launch-configuration errors only; never synchronises
+    if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return RN_OK;
+}
+
+extern "C" const char *rn_last_error(void) { return g_err; }
+extern "C" int rn_abi_version(void) { return 1; }
+
+extern "C" int rn_num_anchors(int H, int W, int K) {
+    if (H <= 0 || W <= 0 || K <= 0) return 0;
+    long long cells = 0;
+    for (int l = 3; l < 3 + RN_NUM_LEVELS; ++l) {
+        long long s = 1LL << l;
+        cells += ((H + s - 1) / s) * ((W + s - 1) / s);  // retinanet.py:488
+    }
+    long long a = cells * K;
+    return a > 0x7fffffffLL ? 0 : (int)a;
+}
+
+// Fills the geometry either from (H, W, base, K) or, in table mode (anchors != NULL), just A.
+int rn_build_geom(RnGeom *g, int H, int W, const double *base, int K, const float *anchors, int A) {
+    memset(g, 0, sizeof(*g));
+    g->H = H;
+    g->W = W;
+    g->A = A;
+    g->K = K > 0 ? K : 1;
+    if (anchors) {
+        if (A <= 0) return rn_set_error(RN_ERR_INVALID_ARG, "anchor table given but A=%d", A);
+        return RN_OK;
+    }
+    if (!base) return rn_set_error(RN_ERR_INVALID_ARG, "neither an anchor table nor a base table was given");
+    if (K < 1 || K > RN_MAX_K) return rn_set_error(RN_ERR_INVALID_ARG, "K=%d outside [1,%d]", K, RN_MAX_K);
+    if (H <= 0 || W <= 0) return rn_set_error(RN_ERR_INVALID_ARG, "bad image size %dx%d", H, W);
+    int expect = rn_num_anchors(H, W, K);
+    if (expect <= 0 || expect != A)
+        return rn_set_error(RN_ERR_INVALID_ARG, "A=%d does not match the %d anchors of a %dx%d image with K=%d", A,
+                            expect, H, W, K);
+    int off = 0;
+    for (int l = 0; l < RN_NUM_LEVELS; ++l) {
+        int s = 8 << l;
+        g->gh[l] = (H + s - 1) / s;
+        g->gw[l] = (W + s - 1) / s;
+        g->off[l] = off;
+        off += g->gh[l] * g->gw[l] * K;
+        for (int k = 0; k < K; ++k)
+            for (int j = 0; j < 4; ++j) g->base[(l * RN_MAX_K + k) * 4 + j] = base[(l * K + k) * 4 + j];
+    }
+    g->off[RN_NUM_LEVELS] = off;
+    return RN_OK;
+}

@@ -1,0 +1,411 @@
+// rn_loss.cu -- sigmoid-focal + smooth-L1 loss, forward AND backward in one streaming pass.
+//
+// Replaces (reference file:line): ssd1 Vision.py:1568-1605 (one-hot build, gathers), focal_loss_retina
+// Vision.py:1513-1530, smoothL1_loss_retina Vision.py:1532-1566, SSD_loss.__call__ Vision.py:1620-1644
+// and the autograd replay of all of it (General/Learner.py:514).
+//
+// Data movement: clas [B,A,C] is read once and dclas written once with 128-bit accesses in a flat,
+// perfectly coalesced mapping (a row of C floats is C/4 vectors; the row index is recovered with a
+// compile-time-constant division); reg is only read for positive anchors; dreg is written once.
+// Algorithmic bytes per image: 8*A*(C+4) with gradients, 4*A*(C+4) forward only.  The kernel is
+// HBM-bound by design but sits close to the fp32 issue limit (~28 instructions per class element), so
+// the logarithm is a branch-free polynomial (no special cases are reachable: its argument is clamped
+// to [1e-4, 1-1e-4]) and the one division per element is MUFU.RCP + FMUL.  No tensor cores: there is no
+// contraction anywhere on this path.
+//
+// Reductions: per-thread fp32 partial sums over <= 32 elements, fixed-order warp/block trees, one
+// partial per CTA, then a single-CTA final kernel that sums the partials of each image in a fixed
+// order in float64.  No floating-point atomics anywhere => run-to-run bit-identical results.
+#include "rn_common.cuh"
+
+#define RN_LOSS_U 8  // vectors per thread
+#define RN_LOSS_TILE (RN_THREADS * RN_LOSS_U)
+
+struct RnLossParams {
+    const float *clas;
+    const float *reg;
+    const float4 *gt_boxes;
+    const int64_t *gt_cats;
+    const int32_t *matches;
+    const int32_t *npos;
+    const float4 *table;
+    float *dclas;
+    float *dreg;
+    float *partials;  // [B][tiles][2] : {sum of focal terms, sum of smooth-L1 terms}
+    int B, A, C, CV, M, tiles;
+    float a_pos, a_neg, gamma, lo, hi;
+    float wc_over_bs, wr_over_bs;  // beta / B_global, (1-beta) / B_global   (Vision.py:1644)
+};
+
+// -2*log(v) for v in [2^-20, 1]; max relative error 1.5e-7 (degree-6 minimax on [sqrt(.5), sqrt(2)),
+// fitted for the relative error of log itself).  Branch free, no special cases.
+__device__ __forceinline__ float rn_neg2log(float v) {
+    const int i = __float_as_int(v);
+    const int t = (i - 0x3f3504f3) & 0xff800000;  // exponent (as a float-field multiple of 2^23)
+    const float f = __int_as_float(i - t) - 1.0f;  // mantissa in [sqrt(.5), sqrt(2)) minus 1
+    const float e23 = (float)t;
+    float p = -2.0f * 8.700362962e-02f;
+    p = fmaf(p, f, -2.0f * -1.426749380e-01f);
+    p = fmaf(p, f, -2.0f * 1.491478973e-01f);
+    p = fmaf(p, f, -2.0f * -1.657758280e-01f);
+    p = fmaf(p, f, -2.0f * 1.996306205e-01f);
+    p = fmaf(p, f, -2.0f * -2.500133718e-01f);
+    p = fmaf(p, f, -2.0f * 3.333391077e-01f);
+    const float z = f * f;
+    const float w0 = fmaf(-2.0f, f, z);  // -2*(f - f^2/2)
+    const float r = fmaf(z * f, p, w0);
+    return fmaf(e23, -2.0f * 0.69314718056f / 8388608.0f, r);
+}
+
+__device__ __forceinline__ float rn_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// One class element.  POS selects the target (t = 1 for the matched class of a positive anchor).
+// Returns the gradient w.r.t. the probability (already scaled by `ga` = alpha-weight * upstream) and
+// adds the focal term divided by (alpha-weight/2) to `acc`.
+//   t = 0:  l = -(1-a) r^g log(q),  dl/dp = (1-a) ( r^g / q - g r^(g-1) log q ),  r = 1-(1-p), q = 1-p
+//   t = 1:  l = -a q^g log(p),      dl/dp = -a ( q^g / p - g q^(g-1) log p )
+// (r, not p, on purpose: the reference computes (1-pt) with pt = 1-p in fp32, Vision.py:1525-1527.)
+template <bool POS, bool G2, bool GRAD>
+__device__ __forceinline__ float rn_focal_elem(float x, float lo, float hi, float gamma, float ga, float &acc) {
+    const float p = fminf(fmaxf(x, lo), hi);  // Vision.py:1524
+    const float q = 1.0f - p;
+    const float u = POS ? q : (1.0f - q);
+    const float v = POS ? p : q;
+    const float l2 = rn_neg2log(v);  // -2 log v  >= 0
+    float pw, pw1;
+    if (G2) {
+        pw1 = u;
+        pw = u * u;  // pow(x, 2.0) == x*x in torch
+    } else {
+        pw1 = powf(u, gamma - 1.0f);
+        pw = pw1 * u;
+    }
+    acc = fmaf(pw, l2, acc);
+    if (!GRAD) return 0.0f;
+    // pw / v - gamma * pw1 * log v  =  pw * rcp(v) + (gamma/2) * pw1 * l2
+    float g = G2 ? fmaf(pw1, l2, pw * rn_rcp_approx(v)) : fmaf(0.5f * gamma * pw1, l2, pw * rn_rcp_approx(v));
+    g *= POS ? -ga : ga;
+    return (p == x) ? g : 0.0f;  // clamp backward: pass-through iff lo <= x <= hi (inclusive)
+}
+
+template <int V>
+struct RnVec;
+template <>
+struct RnVec<4> {
+    float4 d;
+    __device__ __forceinline__ void load(const float *p) { d = rn_ldg_stream(reinterpret_cast<const float4 *>(p)); }
+    __device__ __forceinline__ void store(float *p) const { rn_stg_stream(reinterpret_cast<float4 *>(p), d); }
+    __device__ __forceinline__ float &at(int e) { return e == 0 ? d.x : (e == 1 ? d.y : (e == 2 ? d.z : d.w)); }
+};
+template <>
+struct RnVec<1> {
+    float d;
+    __device__ __forceinline__ void load(const float *p) { d = __ldg(p); }
+    __device__ __forceinline__ void store(float *p) const { *p = d; }
+    __device__ __forceinline__ float &at(int) { return d; }
+};
+
+// V: floats per vector (4 when C % 4 == 0, else 1).  CVT: compile-time vectors per row (0 = runtime).
+template <int V, int CVT, bool G2, bool GRAD>
+__global__ void __launch_bounds__(RN_THREADS)
+rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ RnGeom g) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    // layout: base doubles | gt boxes float4[M] | gt cats int[M]
+    double *s_base = reinterpret_cast<double *>(smem);
+    float4 *s_box = reinterpret_cast<float4 *>(smem + sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4);
+    int *s_cat = reinterpret_cast<int *>(s_box + P.M);
+    __shared__ float s_red[2][RN_THREADS / 32];
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int A = P.A;
+    const int CV = CVT ? CVT : P.CV;
+    const int nvec = A * CV;  // vectors in one image
+    const int tile0 = blockIdx.x * RN_LOSS_TILE;
+
+    if (!P.table) rn_stage_base(g, s_base);
+    if (tid < 32) rn_compact_gt(P.gt_boxes + (size_t)b * P.M, P.gt_cats + (size_t)b * P.M, P.M, s_box, nullptr, s_cat);
+
+    const int n_pos = P.npos[b];
+    const float n_norm = fmaxf((float)n_pos, 1.0f);                  // clamp(min=1), Vision.py:1530
+    const float gl = __fdiv_rn(P.wc_over_bs, n_norm);                // upstream of every focal term
+    const float *x_img = P.clas + (size_t)b * A * P.C;
+    float *dx_img = GRAD ? P.dclas + (size_t)b * A * P.C : nullptr;
+    const int32_t *m_img = P.matches + (size_t)b * A;
+
+    // ---- issue all loads of the tile first (U independent 128-bit loads per thread) ----
+    RnVec<V> xv[RN_LOSS_U];
+    int mrow[RN_LOSS_U];
+#pragma unroll
+    for (int u = 0; u < RN_LOSS_U; ++u) {
+        const int v = tile0 + u * RN_THREADS + tid;
+        if (v < nvec) {
+            xv[u].load(x_img + (size_t)v * V);
+            mrow[u] = __ldg(m_img + v / CV);
+        } else {
+            mrow[u] = RN_MATCH_IGNORE;
+#pragma unroll
+            for (int e = 0; e < V; ++e) xv[u].at(e) = 0.5f;
+        }
+    }
+    __syncthreads();  // s_cat / s_box / s_base visible
+
+    float acc_neg = 0.0f, acc_pos = 0.0f;
+#pragma unroll
+    for (int u = 0; u < RN_LOSS_U; ++u) {
+        const int v = tile0 + u * RN_THREADS + tid;
+        const int m = mrow[u];
+        const float a_row = (m == RN_MATCH_IGNORE) ? 0.0f : P.a_neg;  // ignored anchors contribute nothing
+        const float ga = a_row * gl;
+        int pe = -1;  // element of this vector that is the positive class, if any
+        if (m >= 0) {
+            const int row = v / CV;
+            pe = s_cat[m] - (v - row * CV) * V;  // Vision.py:1588-1593
+        }
+        float part = 0.0f;
+        RnVec<V> gv;
+        if ((unsigned)pe >= (unsigned)V) {  // common case: every element has target 0
+#pragma unroll
+            for (int e = 0; e < V; ++e) gv.at(e) = rn_focal_elem<false, G2, GRAD>(xv[u].at(e), P.lo, P.hi, P.gamma, ga, part);
+        } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                if (e == pe) {
+                    float pp = 0.0f;
+                    gv.at(e) = rn_focal_elem<true, G2, GRAD>(xv[u].at(e), P.lo, P.hi, P.gamma, P.a_pos * gl, pp);
+                    acc_pos = fmaf(0.5f * P.a_pos, pp, acc_pos);
+                } else {
+                    gv.at(e) = rn_focal_elem<false, G2, GRAD>(xv[u].at(e), P.lo, P.hi, P.gamma, ga, part);
+                }
+            }
+        }
+        acc_neg = fmaf(0.5f * a_row, part, acc_neg);
+        if (GRAD && v < nvec) gv.store(dx_img + (size_t)v * V);
+    }
+
+    // ---- regression rows whose first vector lies in this tile: smooth L1 (Vision.py:1532-1566) ----
+    float acc_reg = 0.0f;
+    {
+        const int r0 = (tile0 + CV - 1) / CV;
+        const int r1 = min(A, (tile0 + RN_LOSS_TILE + CV - 1) / CV);
+        const float numel = (float)(4 * n_pos);
+        const float ge = n_pos > 0 ? __fdiv_rn(P.wr_over_bs, numel) : 0.0f;  // mean() backward
+        const float4 *reg4 = reinterpret_cast<const float4 *>(P.reg) + (size_t)b * A;
+        float4 *dreg4 = GRAD ? reinterpret_cast<float4 *>(P.dreg) + (size_t)b * A : nullptr;
+        const float knee = (float)(1.0 / 9.0), off = (float)(0.5 / 9.0);  // Vision.py:1565
+        for (int row = r0 + tid; row < r1; row += RN_THREADS) {
+            const int m = __ldg(m_img + row);
+            float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m >= 0) {
+                const float4 an = rn_anchor(g, s_base, P.table, row);
+                const float4 tg = s_box[m];
+                const float4 pr = __ldg(reg4 + row);
+                const float aw = __fsub_rn(an.z, an.x), ah = __fsub_rn(an.w, an.y);
+                const float acx = __fadd_rn(an.x, __fmul_rn(0.5f, aw)), acy = __fadd_rn(an.y, __fmul_rn(0.5f, ah));
+                float tw = __fsub_rn(tg.z, tg.x), th = __fsub_rn(tg.w, tg.y);
+                const float tcx = __fadd_rn(tg.x, __fmul_rn(0.5f, tw)), tcy = __fadd_rn(tg.y, __fmul_rn(0.5f, th));
+                tw = fmaxf(tw, 1.0f);  // Vision.py:1553-1554
+                th = fmaxf(th, 1.0f);
+                float ts[4], pv[4] = {pr.x, pr.y, pr.z, pr.w}, gg[4];
+                ts[0] = __fdiv_rn(__fdiv_rn(__fsub_rn(tcx, acx), aw), 0.1f);  // Vision.py:1556, :1562
+                ts[1] = __fdiv_rn(__fdiv_rn(__fsub_rn(tcy, acy), ah), 0.1f);
+                ts[2] = __fdiv_rn(logf(__fdiv_rn(tw, aw)), 0.2f);             // Vision.py:1558
+                ts[3] = __fdiv_rn(logf(__fdiv_rn(th, ah)), 0.2f);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float d = __fsub_rn(ts[k], pv[k]);
+                    const float diff = fabsf(d);
+                    float l, gd;
+                    if (diff < knee) {
+                        l = __fmul_rn(4.5f, __fmul_rn(diff, diff));
+                        gd = __fmul_rn(__fmul_rn(ge, 4.5f), __fmul_rn(2.0f, diff));
+                    } else {
+                        l = __fsub_rn(diff, off);
+                        gd = ge;
+                    }
+                    acc_reg += l;
+                    gg[k] = d > 0.0f ? -gd : (d < 0.0f ? gd : 0.0f);  // -sign(t - p) * gd
+                }
+                g4 = make_float4(gg[0], gg[1], gg[2], gg[3]);
+            }
+            if (GRAD) dreg4[row] = g4;
+        }
+    }
+
+    // ---- block reduction (fixed order) -> one partial pair per CTA ----
+    float c = rn_warp_sum(acc_neg + acc_pos);
+    float r = rn_warp_sum(acc_reg);
+    if ((tid & 31) == 0) {
+        s_red[0][tid >> 5] = c;
+        s_red[1][tid >> 5] = r;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float cs = 0.f, rs = 0.f;
+#pragma unroll
+        for (int w = 0; w < RN_THREADS / 32; ++w) {
+            cs += s_red[0][w];
+            rs += s_red[1][w];
+        }
+        float2 *out = reinterpret_cast<float2 *>(P.partials) + ((size_t)b * P.tiles + blockIdx.x);
+        *out = make_float2(cs, rs);
+    }
+}
+
+// One CTA: per image, sum the CTA partials in a fixed order in float64, normalise like the reference
+// (Vision.py:1530, :1566), accumulate over images in fp32 in image order (Vision.py:1640-1641) and
+// combine (Vision.py:1643-1644).
+__global__ void __launch_bounds__(1024)
+rn_loss_final_kernel(const float2 *__restrict__ partials, const int32_t *__restrict__ npos, int B, int tiles,
+                     float w_reg, float w_clas, float bs, float *__restrict__ per_image /*[B][2]*/,
+                     float *__restrict__ out3) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int b = warp; b < B; b += nwarps) {
+        double cs = 0.0, rs = 0.0;
+        for (int t = lane; t < tiles; t += 32) {
+            float2 p = partials[(size_t)b * tiles + t];
+            cs += (double)p.x;
+            rs += (double)p.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cs += __shfl_xor_sync(RN_FULL_MASK, cs, o);
+            rs += __shfl_xor_sync(RN_FULL_MASK, rs, o);
+        }
+        if (lane == 0) {
+            const int n = npos[b];
+            const float n_norm = fmaxf((float)n, 1.0f);
+            per_image[2 * b + 0] = n > 0 ? __fdiv_rn((float)rs, (float)(4 * n)) : 0.0f;  // reg loss of image b
+            per_image[2 * b + 1] = __fdiv_rn((float)cs, n_norm);                          // clas loss of image b
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float reg_total = 0.f, clas_total = 0.f;
+        for (int b = 0; b < B; ++b) {
+            reg_total = __fadd_rn(reg_total, per_image[2 * b + 0]);
+            clas_total = __fadd_rn(clas_total, per_image[2 * b + 1]);
+        }
+        const float reg_loss = __fdiv_rn(reg_total, bs), clas_loss = __fdiv_rn(clas_total, bs);
+        out3[0] = __fadd_rn(__fmul_rn(w_reg, reg_loss), __fmul_rn(w_clas, clas_loss));
+        out3[1] = reg_loss;
+        out3[2] = clas_loss;
+    }
+}
+
+// In-place scale by a device scalar; exits at once when the scalar is exactly 1.
+__global__ void __launch_bounds__(RN_THREADS)
+rn_scale_kernel(float *__restrict__ a, size_t na, float *__restrict__ bptr, size_t nb, const float *__restrict__ s) {
+    const float k = *s;
+    if (k == 1.0f) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 *a4 = reinterpret_cast<float4 *>(a);
+    for (size_t i = i0; i < na / 4; i += stride) {
+        float4 v = a4[i];
+        v.x *= k; v.y *= k; v.z *= k; v.w *= k;
+        a4[i] = v;
+    }
+    for (size_t i = (na / 4) * 4 + i0; i < na; i += stride) a[i] *= k;
+    float4 *b4 = reinterpret_cast<float4 *>(bptr);
+    for (size_t i = i0; i < nb / 4; i += stride) {
+        float4 v = b4[i];
+        v.x *= k; v.y *= k; v.z *= k; v.w *= k;
+        b4[i] = v;
+    }
+    for (size_t i = (nb / 4) * 4 + i0; i < nb; i += stride) bptr[i] *= k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static int rn_loss_tiles(int A, int C) {
+    const int V = (C % 4 == 0) ? 4 : 1;
+    const long long nvec = (long long)A * (C / V);
+    return (int)((nvec + RN_LOSS_TILE - 1) / RN_LOSS_TILE);
+}
+
+extern "C" size_t rn_loss_workspace_bytes(int B, int A, int C) {
+    if (B <= 0 || A <= 0 || C <= 0) return 256;
+    size_t partials = sizeof(float2) * (size_t)B * (size_t)rn_loss_tiles(A, C);
+    size_t per_image = sizeof(float) * 2 * (size_t)B;
+    return ((partials + 255) / 256) * 256 + ((per_image + 255) / 256) * 256;
+}
+
+template <int V, int CVT>
+static void rn_launch_loss(bool g2, bool grad, dim3 grid, size_t smem, cudaStream_t s, const RnLossParams &P,
+                           const RnGeom &g) {
+    if (g2 && grad) rn_loss_kernel<V, CVT, true, true><<<grid, RN_THREADS, smem, s>>>(P, g);
+    else if (g2) rn_loss_kernel<V, CVT, true, false><<<grid, RN_THREADS, smem, s>>>(P, g);
+    else if (grad) rn_loss_kernel<V, CVT, false, true><<<grid, RN_THREADS, smem, s>>>(P, g);
+    else rn_loss_kernel<V, CVT, false, false><<<grid, RN_THREADS, smem, s>>>(P, g);
+}
+
+extern "C" int rn_loss(const float *clas, const float *reg, const float *gt_boxes, const int64_t *gt_cats,
+                       const int32_t *matches, const int32_t *npos, int B, int A, int C, int M, int H, int W,
+                       const double *base, int K, const float *anchors, double alpha, double gamma, double beta,
+                       int B_global, float *dclas, float *dreg, float *out3, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+    if (B <= 0 || A <= 0 || C <= 0 || M < 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: B=%d A=%d C=%d M=%d", B, A, C, M);
+    if (!clas || !reg || !matches || !npos || !out3 || (M > 0 && (!gt_boxes || !gt_cats)))
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: null pointer");
+    if ((dclas == nullptr) != (dreg == nullptr))
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: dclas and dreg must both be given or both be NULL");
+    if (B_global < B) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: B_global=%d < B=%d", B_global, B);
+    const int V = (C % 4 == 0) ? 4 : 1;
+    if ((long long)A * (C / V) > 0x7fffffffLL - RN_LOSS_TILE) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: A*C too large");
+    if (V == 4 && ((((uintptr_t)clas) | ((uintptr_t)dclas)) & 15))
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: clas/dclas must be 16-byte aligned");
+    if ((((uintptr_t)reg) | ((uintptr_t)dreg) | ((uintptr_t)gt_boxes) | ((uintptr_t)anchors)) & 15)
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: reg/dreg/gt_boxes/anchors must be 16-byte aligned");
+    if (workspace_bytes < rn_loss_workspace_bytes(B, A, C) || !workspace || (((uintptr_t)workspace) & 255))
+        return rn_set_error(RN_ERR_WORKSPACE, "rn_loss: workspace needs %zu bytes, 256-byte aligned", rn_loss_workspace_bytes(B, A, C));
+    RnGeom g;
+    int rc = rn_build_geom(&g, H, W, base, K, anchors, A);
+    if (rc) return rc;
+
+    const int tiles = rn_loss_tiles(A, C);
+    RnLossParams P;
+    P.clas = clas; P.reg = reg;
+    P.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); P.gt_cats = gt_cats;
+    P.matches = matches; P.npos = npos; P.table = reinterpret_cast<const float4 *>(anchors);
+    P.dclas = dclas; P.dreg = dreg;
+    P.partials = reinterpret_cast<float *>(workspace);
+    P.B = B; P.A = A; P.C = C; P.CV = C / V; P.M = M; P.tiles = tiles;
+    P.a_pos = (float)alpha; P.a_neg = (float)(1.0 - alpha);  // Vision.py:1526
+    P.gamma = (float)gamma;
+    P.lo = (float)1e-4; P.hi = (float)(1.0 - 1e-4);          // Vision.py:1524
+    const float bs = (float)B_global;
+    const float w_reg = (float)(1.0 - beta), w_clas = (float)beta;  // Vision.py:1644
+    P.wc_over_bs = w_clas / bs;
+    P.wr_over_bs = w_reg / bs;
+    float *per_image = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(workspace) +
+                                                 ((sizeof(float2) * (size_t)B * tiles + 255) / 256) * 256);
+
+    const size_t smem = sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4 + (size_t)M * (sizeof(float4) + sizeof(int));
+    if (smem > 48 * 1024) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: M=%d too large", M);
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid(tiles, B);
+    const bool g2 = (gamma == 2.0), grad = dclas != nullptr;
+    if (V == 4 && C == 80) rn_launch_loss<4, 20>(g2, grad, grid, smem, s, P, g);
+    else if (V == 4 && C == 20) rn_launch_loss<4, 5>(g2, grad, grid, smem, s, P, g);
+    else if (V == 4) rn_launch_loss<4, 0>(g2, grad, grid, smem, s, P, g);
+    else rn_launch_loss<1, 0>(g2, grad, grid, smem, s, P, g);
+    rc = rn_check_launch("rn_loss");
+    if (rc) return rc;
+    rn_loss_final_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const float2 *>(P.partials), npos, B, tiles, w_reg,
+                                            w_clas, bs, per_image, out3);
+    return rn_check_launch("rn_loss_final");
+}
+
+extern "C" int rn_scale_grads(float *dclas, size_t n_clas, float *dreg, size_t n_reg, const float *grad_out,
+                              void *stream) {
+    if (!grad_out || (n_clas && !dclas) || (n_reg && !dreg)) return rn_set_error(RN_ERR_INVALID_ARG, "rn_scale_grads: null pointer");
+    if ((((uintptr_t)dclas) | ((uintptr_t)dreg)) & 15) return rn_set_error(RN_ERR_INVALID_ARG, "rn_scale_grads: 16-byte alignment required");
+    rn_scale_kernel<<<148 * 8, RN_THREADS, 0, (cudaStream_t)stream>>>(dclas, n_clas, dreg, n_reg, grad_out);
+    return rn_check_launch("rn_scale_grads");
+}

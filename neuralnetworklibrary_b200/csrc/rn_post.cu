@@ -1,0 +1,547 @@
+// rn_post.cu -- inference post-processing: class max, threshold, decode, clip, top-k, bitmask NMS.
+//
+// Replaces (reference file:line): BBoxPredictor.__call__ retinanet.py:732-812 and nms
+// retinanet.py:523-711 with rel_thresh/inc/dup = None (those three optional stages act on the <= top_k
+// survivors and stay on the host, see neuralnetworklibrary_b200/retinanet.py).
+//
+// Pipeline (all on the caller's stream, no host synchronisation):
+//   K3a rn_post_scan_kernel   HBM-bound: streams clas [B,A,C] once with 128-bit loads, L lanes per
+//                             anchor row, warp-shuffle (max, first-argmax); rows over the threshold
+//                             are decoded + clipped (reg row is read only for them) and appended as
+//                             64-bit keys {sortable score | ~anchor} with one warp-aggregated atomic.
+//   K3b rn_post_select_kernel one CTA per image: exact top-k of the keys (radix select on 11-bit
+//                             digits until the survivors fit in shared memory, then a bitonic sort).
+//                             Keys are unique, so the order (score desc, anchor asc) is total.
+//   K3c rn_post_nms_kernel    one CTA per image: re-derives class/box of the <= top_k selected anchors,
+//                             builds the class-aware suppression bitmask (IoU in strict fp32), one warp
+//                             sweeps it visiting only kept boxes, first max_keep survivors are written.
+// Algorithmic bytes per image: 4*A*(C+4) (clas + reg read); everything after K3a touches O(top_k^2).
+#include "rn_common.cuh"
+
+#define RN_SORT_N RN_MAX_TOP_K  // keys that fit the shared-memory sort
+#define RN_SEL_THREADS 1024
+#define RN_DIGIT_BITS 11
+#define RN_BINS (1 << RN_DIGIT_BITS)
+
+struct RnDecode {
+    float mean[4], std[4];
+    float img_w, img_h;
+};
+
+// Decode + clip one anchor: retinanet.py:750-753 (anchor centre form), :772-785 (shift), :790-793
+// (the four one-sided clamps).  Every op is individually rounded like the reference's tensor ops.
+__device__ __forceinline__ float4 rn_decode(float4 an, float4 rg, const RnDecode &d) {
+    const float w = __fsub_rn(an.z, an.x), h = __fsub_rn(an.w, an.y);
+    const float cx = __fadd_rn(an.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(an.y, __fmul_rn(0.5f, h));
+    const float dx = __fadd_rn(__fmul_rn(rg.x, d.std[0]), d.mean[0]);
+    const float dy = __fadd_rn(__fmul_rn(rg.y, d.std[1]), d.mean[1]);
+    const float dw = __fadd_rn(__fmul_rn(rg.z, d.std[2]), d.mean[2]);
+    const float dh = __fadd_rn(__fmul_rn(rg.w, d.std[3]), d.mean[3]);
+    const float pcx = __fadd_rn(cx, __fmul_rn(w, dx)), pcy = __fadd_rn(cy, __fmul_rn(h, dy));
+    const float pw = __fmul_rn(w, expf(dw)), ph = __fmul_rn(h, expf(dh));
+    float4 b;
+    b.x = fmaxf(__fsub_rn(pcx, __fmul_rn(0.5f, pw)), 0.0f);
+    b.y = fmaxf(__fsub_rn(pcy, __fmul_rn(0.5f, ph)), 0.0f);
+    b.z = fminf(__fadd_rn(pcx, __fmul_rn(0.5f, pw)), d.img_w);
+    b.w = fminf(__fadd_rn(pcy, __fmul_rn(0.5f, ph)), d.img_h);
+    return b;
+}
+
+__device__ __forceinline__ bool rn_box_nonempty(float4 b) {  // retinanet.py:796-798
+    return (__fsub_rn(b.z, b.x) > 0.0f) && (__fsub_rn(b.w, b.y) > 0.0f);
+}
+
+__device__ __forceinline__ void rn_argmax_update(float v, int c, float &best, int &bc) {
+    if (v > best) {  // strict: lowest class index wins ties (torch.max(dim=1), retinanet.py:759)
+        best = v;
+        bc = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3a
+// ------------------------------------------------------------------------------------------------
+#define RN_SCAN_STEPS 4
+
+// V = floats per load (4 or 1), L = lanes per anchor row (4 or 1).
+template <int V, int L>
+__global__ void __launch_bounds__(RN_THREADS)
+rn_post_scan_kernel(const float *__restrict__ clas, const float *__restrict__ reg, int C,
+                    const __grid_constant__ RnGeom g, const float4 *__restrict__ table,
+                    const __grid_constant__ RnDecode dec, float thresh, unsigned long long *__restrict__ keys,
+                    int32_t *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double *s_base = reinterpret_cast<double *>(smem);
+    if (!table) rn_stage_base(g, s_base);
+    __syncthreads();
+
+    const int b = blockIdx.y, A = g.A;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane % L;           // position inside the row group
+    const int rows_per_warp = 32 / L;
+    const int rows_per_cta = (RN_THREADS / 32) * rows_per_warp * RN_SCAN_STEPS;
+    const int CV = C / V;
+    const float *clas_b = clas + (size_t)b * A * C;
+
+#pragma unroll 1
+    for (int step = 0; step < RN_SCAN_STEPS; ++step) {
+        const int a = blockIdx.x * rows_per_cta + (step * (RN_THREADS / 32) + warp) * rows_per_warp + lane / L;
+        float best = -INFINITY;
+        int bc = 0;
+        if (a < A) {
+            const float *row = clas_b + (size_t)a * C;
+            if (V == 4) {
+                const float4 *row4 = reinterpret_cast<const float4 *>(row);
+#pragma unroll 5
+                for (int j = sub; j < CV; j += L) {
+                    const float4 x = (L == 1) ? __ldg(row4 + j) : rn_ldg_stream(row4 + j);
+                    rn_argmax_update(x.x, 4 * j + 0, best, bc);
+                    rn_argmax_update(x.y, 4 * j + 1, best, bc);
+                    rn_argmax_update(x.z, 4 * j + 2, best, bc);
+                    rn_argmax_update(x.w, 4 * j + 3, best, bc);
+                }
+            } else {
+                for (int j = sub; j < CV; j += L) rn_argmax_update(__ldg(row + j), j, best, bc);
+            }
+        }
+        if (L > 1) {  // combine the L lanes of a row: larger value, then lower class index
+#pragma unroll
+            for (int o = L / 2; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(RN_FULL_MASK, best, o);
+                const int oc = __shfl_xor_sync(RN_FULL_MASK, bc, o);
+                if (ov > best || (ov == best && oc < bc)) {
+                    best = ov;
+                    bc = oc;
+                }
+            }
+        }
+        bool ok = (a < A) && (sub == 0) && (best > thresh);  // strict, retinanet.py:760
+        if (ok) {
+            const float4 an = rn_anchor(g, s_base, table, a);
+            const float4 rg = __ldg(reinterpret_cast<const float4 *>(reg) + (size_t)b * A + a);
+            ok = rn_box_nonempty(rn_decode(an, rg, dec));
+        }
+        const unsigned m = __ballot_sync(RN_FULL_MASK, ok);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            int basepos = 0;
+            if (lane == leader) basepos = atomicAdd(counts + b, __popc(m));
+            basepos = __shfl_sync(RN_FULL_MASK, basepos, leader);
+            if (ok) {
+                const int pos = basepos + __popc(m & ((1u << lane) - 1u));
+                keys[(size_t)b * A + pos] =
+                    ((unsigned long long)rn_float_sortable(best) << 32) | (unsigned long long)(0xffffffffu - (unsigned)a);
+            }
+        }
+    }
+}
+
+// Keys for caller-provided scores (rn_nms).
+__global__ void rn_make_keys_kernel(const float *__restrict__ scores, int n, unsigned long long *__restrict__ keys,
+                                    int32_t *__restrict__ count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ((unsigned long long)rn_float_sortable(scores[i]) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+    if (i == 0) *count = n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b: exact top-k of unique 64-bit keys, sorted descending
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int rn_block_excl_scan_1024(int v, int *s_warp /*[32]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(RN_FULL_MASK, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(RN_FULL_MASK, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_warp[lane] = winc - w;  // exclusive prefix of warp totals
+    }
+    __syncthreads();
+    const int r = s_warp[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(RN_SEL_THREADS)
+rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t *__restrict__ counts, int cap,
+                      int top_k, unsigned long long *__restrict__ sel, int32_t *__restrict__ nsel) {
+    __shared__ unsigned long long s_keys[RN_SORT_N];
+    __shared__ int s_hist[RN_BINS];
+    __shared__ int s_warp[32];
+    __shared__ int s_digit, s_above, s_bincnt, s_n;
+
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const unsigned long long *kb = keys + (size_t)b * cap;
+    const int n = min(counts[b], cap);
+    const int K = min(top_k, n);
+    if (tid == 0) nsel[b] = K;
+    if (K == 0) return;
+
+    int total;  // keys staged in s_keys
+    if (n <= RN_SORT_N) {
+        for (int i = tid; i < n; i += RN_SEL_THREADS) s_keys[i] = kb[i];
+        total = n;
+    } else {
+        // radix select from the most significant digit down until (#certain + #in-bin) fits
+        unsigned long long prefix = 0;
+        int done = 0, need = K, above_total = 0;
+        while (true) {
+            const int db = min(RN_DIGIT_BITS, 64 - done);
+            const int shift = 64 - done - db;
+            for (int i = tid; i < RN_BINS; i += RN_SEL_THREADS) s_hist[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < n; i += RN_SEL_THREADS) {
+                const unsigned long long k = kb[i];
+                if (done == 0 || (k >> (64 - done)) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & ((1u << db) - 1u))], 1);
+            }
+            __syncthreads();
+            // bins in descending digit order: thread t owns ranks 2t and 2t+1
+            const int d0 = RN_BINS - 1 - 2 * tid, d1 = d0 - 1;
+            const int c0 = s_hist[d0], c1 = s_hist[d1];
+            const int ex = rn_block_excl_scan_1024(c0 + c1, s_warp);
+            if (ex < need && need <= ex + c0) {
+                s_digit = d0; s_above = ex; s_bincnt = c0;
+            } else if (ex + c0 < need && need <= ex + c0 + c1) {
+                s_digit = d1; s_above = ex + c0; s_bincnt = c1;
+            }
+            __syncthreads();
+            above_total += s_above;
+            need -= s_above;
+            prefix = (prefix << db) | (unsigned long long)s_digit;
+            done += db;
+            const int bincnt = s_bincnt;
+            __syncthreads();
+            if (above_total + bincnt <= RN_SORT_N || done == 64) break;
+        }
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += RN_SEL_THREADS) {
+            const unsigned long long k = kb[i];
+            const unsigned long long top = (done == 64) ? k : (k >> (64 - done));
+            if (top >= prefix) {
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < RN_SORT_N) s_keys[pos] = k;
+            }
+        }
+        __syncthreads();
+        total = min(s_n, RN_SORT_N);
+    }
+    int P = 1;
+    while (P < total) P <<= 1;
+    for (int i = total + tid; i < P; i += RN_SEL_THREADS) s_keys[i] = 0ull;  // sorts to the end
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += RN_SEL_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long x = s_keys[i], y = s_keys[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (x < y) : (x > y)) {
+                        s_keys[i] = y;
+                        s_keys[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < K; i += RN_SEL_THREADS) sel[(size_t)b * top_k + i] = s_keys[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3c: gather + bitmask NMS + sweep
+// ------------------------------------------------------------------------------------------------
+struct RnNmsParams {
+    const unsigned long long *sel;  // [B][top_k] sorted keys
+    const int32_t *nsel;            // [B]
+    unsigned long long *mask;       // [B][top_k][words]
+    // FROM_BOXES = false: re-derive from the activations
+    const float *clas, *reg;
+    const float4 *table;
+    int A, C;
+    // FROM_BOXES = true
+    const float4 *boxes_in;
+    const int64_t *classes_in;
+    int top_k, words, max_keep;
+    float max_overlap;
+    // outputs (each may be NULL)
+    float4 *out_boxes;
+    int64_t *out_classes;
+    float *out_scores;
+    int32_t *out_idx;
+    int32_t *out_counts;
+};
+
+template <bool FROM_BOXES>
+__global__ void __launch_bounds__(RN_SEL_THREADS)
+rn_post_nms_kernel(const __grid_constant__ RnNmsParams P, const __grid_constant__ RnGeom g,
+                   const __grid_constant__ RnDecode dec) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    // layout: base doubles | boxes float4[top_k] | area float[top_k] | cls int[top_k] | keep int[top_k]
+    double *s_base = reinterpret_cast<double *>(smem);
+    float4 *s_box = reinterpret_cast<float4 *>(smem + sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4);
+    float *s_area = reinterpret_cast<float *>(s_box + P.top_k);
+    int *s_cls = reinterpret_cast<int *>(s_area + P.top_k);
+    int *s_keep = s_cls + P.top_k;
+    __shared__ int s_nk;
+
+    const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const int K = P.nsel[b];
+    const unsigned long long *sel = P.sel + (size_t)b * P.top_k;
+    if (!FROM_BOXES && !P.table) rn_stage_base(g, s_base);
+    __syncthreads();
+
+    for (int t = tid; t < K; t += nthr) {
+        const unsigned a = 0xffffffffu - (unsigned)(sel[t] & 0xffffffffull);
+        float4 box;
+        int cls;
+        if (FROM_BOXES) {
+            box = P.boxes_in[a];
+            cls = (int)P.classes_in[a];
+        } else {
+            const float *row = P.clas + ((size_t)b * P.A + a) * P.C;
+            float best = -INFINITY;
+            cls = 0;
+            for (int c = 0; c < P.C; ++c) rn_argmax_update(__ldg(row + c), c, best, cls);
+            const float4 an = rn_anchor(g, s_base, P.table, (int)a);
+            const float4 rg = __ldg(reinterpret_cast<const float4 *>(P.reg) + (size_t)b * P.A + a);
+            box = rn_decode(an, rg, dec);
+        }
+        s_box[t] = box;
+        s_area[t] = rn_area(box);
+        s_cls[t] = cls;
+    }
+    __syncthreads();
+
+    // suppression bitmask: bit j of row i  <=>  j > i, same class, IoU(i, j) > max_overlap
+    // (retinanet.py:591-594; rows are in score-descending order)
+    const int words = (K + 63) >> 6;
+    unsigned long long *mask = P.mask + (size_t)b * P.top_k * P.words;
+    for (int item = tid; item < K * words; item += nthr) {
+        const int i = item / words, w = item - i * words;
+        unsigned long long bits = 0ull;
+        if (w * 64 + 63 > i) {
+            const float4 bi = s_box[i];
+            const float ai = s_area[i];
+            const int ci = s_cls[i];
+            const int j0 = max(w * 64, i + 1), j1 = min(w * 64 + 64, K);
+            for (int j = j0; j < j1; ++j) {
+                if (s_cls[j] == ci && rn_iou(bi, ai, s_box[j], s_area[j]) > P.max_overlap) bits |= 1ull << (j & 63);
+            }
+        }
+        mask[(size_t)i * words + w] = bits;
+    }
+    __syncthreads();
+
+    // sweep: one warp, lane l owns removed-words l and l+32 (top_k <= 4096), only kept rows are read
+    if (tid < 32) {
+        const int lane = tid;
+        unsigned long long rem0 = 0ull, rem1 = 0ull;
+        int nk = 0;
+        bool full = P.max_keep <= 0;
+        for (int w = 0; w < words && !full; ++w) {
+            unsigned long long cur = __shfl_sync(RN_FULL_MASK, (w < 32) ? rem0 : rem1, w & 31);
+            const int nbits = min(64, K - w * 64);
+            const unsigned long long valid = (nbits == 64) ? ~0ull : ((1ull << nbits) - 1ull);
+            unsigned long long avail = ~cur & valid;
+            while (avail) {
+                const int bit = __ffsll((long long)avail) - 1;
+                const int i = w * 64 + bit;
+                if (lane == 0) s_keep[nk] = i;
+                ++nk;
+                if (nk >= P.max_keep) {  // later survivors cannot reach the output (retinanet.py:702-704)
+                    full = true;
+                    break;
+                }
+                const unsigned long long *rowm = mask + (size_t)i * words;
+                if (lane < words) rem0 |= rowm[lane];
+                if (lane + 32 < words) rem1 |= rowm[lane + 32];
+                cur = __shfl_sync(RN_FULL_MASK, (w < 32) ? rem0 : rem1, w & 31);
+                const unsigned long long later = (bit == 63) ? 0ull : (~0ull << (bit + 1));
+                avail = ~cur & valid & later;
+            }
+        }
+        if (lane == 0) s_nk = nk;
+    }
+    __syncthreads();
+
+    const int nk = s_nk;
+    if (tid == 0 && P.out_counts) P.out_counts[b] = nk;
+    for (int t = tid; t < nk; t += nthr) {
+        const int i = s_keep[t];
+        const unsigned long long key = sel[i];
+        const size_t o = (size_t)b * P.max_keep + t;
+        if (P.out_boxes) P.out_boxes[o] = s_box[i];
+        if (P.out_classes) P.out_classes[o] = (int64_t)s_cls[i];
+        if (P.out_scores) P.out_scores[o] = rn_sortable_float((uint32_t)(key >> 32));
+        if (P.out_idx) P.out_idx[o] = (int32_t)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static inline size_t rn_up256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct RnPostWs {
+    size_t counts, nsel, keys, sel, mask, total;
+};
+static RnPostWs rn_post_layout(int B, long long cap, int top_k) {
+    RnPostWs w;
+    const size_t words = (size_t)(top_k + 63) / 64;
+    size_t o = 0;
+    w.counts = o; o += rn_up256(sizeof(int32_t) * (size_t)B);
+    w.nsel = o;   o += rn_up256(sizeof(int32_t) * (size_t)B);
+    w.keys = o;   o += rn_up256(sizeof(unsigned long long) * (size_t)B * (size_t)cap);
+    w.sel = o;    o += rn_up256(sizeof(unsigned long long) * (size_t)B * (size_t)top_k);
+    w.mask = o;   o += rn_up256(sizeof(unsigned long long) * (size_t)B * (size_t)top_k * words);
+    w.total = o;
+    return w;
+}
+
+extern "C" size_t rn_postproc_workspace_bytes(int B, int A, int top_k) {
+    if (B <= 0 || A <= 0 || top_k <= 0) return 256;
+    return rn_post_layout(B, A, top_k).total;
+}
+extern "C" size_t rn_nms_workspace_bytes(int n, int top_k) {
+    if (n <= 0 || top_k <= 0) return 256;
+    return rn_post_layout(1, n, top_k).total;
+}
+
+static int rn_launch_select_nms(bool from_boxes, int B, int cap, RnNmsParams &P, const RnGeom &g, const RnDecode &dec,
+                                unsigned char *ws, const RnPostWs &L, cudaStream_t s) {
+    rn_post_select_kernel<<<B, RN_SEL_THREADS, 0, s>>>(reinterpret_cast<unsigned long long *>(ws + L.keys),
+                                                       reinterpret_cast<int32_t *>(ws + L.counts), cap, P.top_k,
+                                                       reinterpret_cast<unsigned long long *>(ws + L.sel),
+                                                       reinterpret_cast<int32_t *>(ws + L.nsel));
+    int rc = rn_check_launch("rn_post_select");
+    if (rc) return rc;
+    P.sel = reinterpret_cast<unsigned long long *>(ws + L.sel);
+    P.nsel = reinterpret_cast<int32_t *>(ws + L.nsel);
+    P.mask = reinterpret_cast<unsigned long long *>(ws + L.mask);
+    P.words = (P.top_k + 63) / 64;
+    const size_t smem = sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4 +
+                        (size_t)P.top_k * (sizeof(float4) + sizeof(float) + 2 * sizeof(int));
+    cudaError_t e;
+    if (from_boxes) {
+        e = cudaFuncSetAttribute(rn_post_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_nms smem: %s", cudaGetErrorString(e));
+        rn_post_nms_kernel<true><<<B, RN_SEL_THREADS, smem, s>>>(P, g, dec);
+    } else {
+        e = cudaFuncSetAttribute(rn_post_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_postproc smem: %s", cudaGetErrorString(e));
+        rn_post_nms_kernel<false><<<B, RN_SEL_THREADS, smem, s>>>(P, g, dec);
+    }
+    return rn_check_launch("rn_post_nms");
+}
+
+extern "C" int rn_postproc(const float *clas, const float *reg, int B, int A, int C, int H, int W, const double *base,
+                           int K, const float *anchors, const float *mean, const float *std, float thresh,
+                           float max_overlap, int top_k, int max_keep, float *boxes, int64_t *classes, float *scores,
+                           int32_t *anchor_idx, int32_t *counts, int32_t *n_candidates, void *workspace,
+                           size_t workspace_bytes, void *stream) {
+    if (B <= 0 || A <= 0 || C <= 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc: B=%d A=%d C=%d", B, A, C);
+    if (!clas || !reg || !mean || !std || !boxes || !classes || !scores || !counts)
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc: null pointer");
+    if (top_k < 1 || top_k > RN_MAX_TOP_K) return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc: top_k=%d outside [1,%d]", top_k, RN_MAX_TOP_K);
+    if (max_keep < 1 || max_keep > top_k) return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc: max_keep=%d outside [1,top_k=%d]", max_keep, top_k);
+    if ((((uintptr_t)reg) | ((uintptr_t)anchors) | ((uintptr_t)boxes)) & 15)
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc: reg/anchors/boxes must be 16-byte aligned");
+    const bool vec = (C % 4 == 0) && ((((uintptr_t)clas) & 15) == 0);
+    const RnPostWs L = rn_post_layout(B, A, top_k);
+    if (!workspace || workspace_bytes < L.total || (((uintptr_t)workspace) & 255))
+        return rn_set_error(RN_ERR_WORKSPACE, "rn_postproc: workspace needs %zu bytes, 256-byte aligned", L.total);
+    RnGeom g;
+    int rc = rn_build_geom(&g, H, W, base, K, anchors, A);
+    if (rc) return rc;
+    RnDecode dec;
+    for (int i = 0; i < 4; ++i) {
+        dec.mean[i] = mean[i];
+        dec.std[i] = std[i];
+    }
+    dec.img_w = (float)W;  // clamp(max=width), retinanet.py:792
+    dec.img_h = (float)H;  // clamp(max=height), retinanet.py:793
+
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    int32_t *d_counts = reinterpret_cast<int32_t *>(ws + L.counts);
+    cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)B, s);
+    if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_postproc memset: %s", cudaGetErrorString(e));
+
+    const size_t smem = sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4;
+    unsigned long long *d_keys = reinterpret_cast<unsigned long long *>(ws + L.keys);
+    const float4 *table = reinterpret_cast<const float4 *>(anchors);
+    if (vec && (C / 4) % 4 == 0) {
+        const int rows = (RN_THREADS / 32) * (32 / 4) * RN_SCAN_STEPS;
+        rn_post_scan_kernel<4, 4><<<dim3((A + rows - 1) / rows, B), RN_THREADS, smem, s>>>(clas, reg, C, g, table, dec, thresh, d_keys, d_counts);
+    } else if (vec) {
+        const int rows = (RN_THREADS / 32) * 32 * RN_SCAN_STEPS;
+        rn_post_scan_kernel<4, 1><<<dim3((A + rows - 1) / rows, B), RN_THREADS, smem, s>>>(clas, reg, C, g, table, dec, thresh, d_keys, d_counts);
+    } else {
+        const int rows = (RN_THREADS / 32) * 32 * RN_SCAN_STEPS;
+        rn_post_scan_kernel<1, 1><<<dim3((A + rows - 1) / rows, B), RN_THREADS, smem, s>>>(clas, reg, C, g, table, dec, thresh, d_keys, d_counts);
+    }
+    rc = rn_check_launch("rn_post_scan");
+    if (rc) return rc;
+
+    RnNmsParams P;
+    memset(&P, 0, sizeof(P));
+    P.clas = clas; P.reg = reg; P.table = table; P.A = A; P.C = C;
+    P.top_k = top_k; P.max_keep = max_keep; P.max_overlap = max_overlap;
+    P.out_boxes = reinterpret_cast<float4 *>(boxes); P.out_classes = classes; P.out_scores = scores;
+    P.out_idx = anchor_idx; P.out_counts = counts;
+    rc = rn_launch_select_nms(false, B, A, P, g, dec, ws, L, s);
+    if (rc) return rc;
+    if (n_candidates) {
+        e = cudaMemcpyAsync(n_candidates, d_counts, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_postproc copy: %s", cudaGetErrorString(e));
+    }
+    return RN_OK;
+}
+
+extern "C" int rn_nms(const float *boxes, const int64_t *classes, const float *scores, int n, float max_overlap,
+                      int top_k, int max_keep, int32_t *keep_idx, int32_t *count, void *workspace,
+                      size_t workspace_bytes, void *stream) {
+    if (n < 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms: n=%d", n);
+    if (!keep_idx || !count) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms: null output");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) {  // retinanet.py:570
+        cudaError_t e0 = cudaMemsetAsync(count, 0, sizeof(int32_t), s);
+        return e0 == cudaSuccess ? RN_OK : rn_set_error(RN_ERR_CUDA, "rn_nms memset: %s", cudaGetErrorString(e0));
+    }
+    if (!boxes || !classes || !scores) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms: null input");
+    if (((uintptr_t)boxes) & 15) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms: boxes must be 16-byte aligned");
+    if (top_k < 1 || top_k > RN_MAX_TOP_K) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms: top_k=%d outside [1,%d]", top_k, RN_MAX_TOP_K);
+    if (max_keep < 1 || max_keep > top_k) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms: max_keep=%d outside [1,top_k=%d]", max_keep, top_k);
+    const RnPostWs L = rn_post_layout(1, n, top_k);
+    if (!workspace || workspace_bytes < L.total || (((uintptr_t)workspace) & 255))
+        return rn_set_error(RN_ERR_WORKSPACE, "rn_nms: workspace needs %zu bytes, 256-byte aligned", L.total);
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    rn_make_keys_kernel<<<(n + 255) / 256, 256, 0, s>>>(scores, n, reinterpret_cast<unsigned long long *>(ws + L.keys),
+                                                        reinterpret_cast<int32_t *>(ws + L.counts));
+    int rc = rn_check_launch("rn_make_keys");
+    if (rc) return rc;
+    RnGeom g;
+    memset(&g, 0, sizeof(g));
+    RnDecode dec;
+    memset(&dec, 0, sizeof(dec));
+    RnNmsParams P;
+    memset(&P, 0, sizeof(P));
+    P.boxes_in = reinterpret_cast<const float4 *>(boxes);
+    P.classes_in = classes;
+    P.top_k = top_k; P.max_keep = max_keep; P.max_overlap = max_overlap;
+    P.out_idx = keep_idx; P.out_counts = count;
+    return rn_launch_select_nms(true, 1, n, P, g, dec, ws, L, s);
+}

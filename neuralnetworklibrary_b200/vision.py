@@ -1,0 +1,221 @@
+"""Drop-in replacements for the bounding-box loss objects of the reference's Applications/Vision.py,
+backed by libretina_sm100.so:
+
+    SSD_loss                  Vision.py:1607-1644  -> rn_assign + rn_loss (+ rn_scale_grads in backward)
+    SSD_RegLoss / SSD_ClasLoss Vision.py:1646-1663 -> read the attributes SSD_loss stores
+    match_anchors_objects     Vision.py:1474-1511  -> rn_assign on one image
+    ComputeMaxOverlaps        Vision.py:1666-1694  -> rn_max_overlaps
+
+`ImageLearner(..., loss_func=SSD_loss())` works unchanged: __call__(activ=[anchors, reg, clas],
+target=[BBoxes, Cats]) returns a 0-dim float32 tensor that is differentiable w.r.t. reg and clas and
+sets .reg_loss / .clas_loss on every call (Vision.py:1643).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .core import ARR, TEN
+from .retinanet import anchor_args
+
+_ws = _lib.Workspace()
+
+
+def _targets(target, device):
+    BBoxes, Cats = target[0], target[1]
+    _lib.require_cuda(BBoxes, "BBoxes")
+    _lib.require_cuda(Cats, "Cats")
+    gt_boxes = BBoxes.detach().to(dtype=torch.float32).contiguous()
+    gt_cats = Cats.detach().to(dtype=torch.int64).contiguous()
+    if gt_boxes.dim() != 3 or gt_boxes.shape[2] != 4 or gt_cats.shape != gt_boxes.shape[:2]:
+        raise ValueError("target must be [BBoxes (bs x M x 4), Cats (bs x M)]")
+    return gt_boxes, gt_cats
+
+
+def assign_batch(anchors, gt_boxes, gt_cats, pos_thresh=0.5, neg_thresh=0.4, want_iou=False):
+    """rn_assign on a batch: returns (matches [B,A] int32, npos [B] int32, max_iou [B,A] or None).
+    matches: >= 0 matched object (index among the image's non-padding rows), -1 background, -2 ignored."""
+    lib = _lib.load()
+    B, M = int(gt_cats.shape[0]), int(gt_cats.shape[1])
+    H, W, base, K, table, A = anchor_args(anchors)
+    dev = gt_boxes.device
+    matches = torch.empty((B, A), dtype=torch.int32, device=dev)
+    npos = torch.empty((B,), dtype=torch.int32, device=dev)
+    miou = torch.empty((B, A), dtype=torch.float32, device=dev) if want_iou else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.rn_assign(_lib.ptr(gt_boxes), _lib.ptr(gt_cats), B, M, H, W, base, K, table, A,
+                                 float(pos_thresh), float(neg_thresh), _lib.ptr(matches), _lib.ptr(npos),
+                                 _lib.ptr(miou), _lib.stream_ptr(dev)))
+    return matches, npos, miou
+
+
+class _SSDLossFunction(torch.autograd.Function):
+    """Forward computes the loss AND both gradients in one streaming pass; backward hands the stored
+    gradients back, scaled on the device by the upstream gradient (a no-op launch when it is 1)."""
+
+    @staticmethod
+    def forward(ctx, reg, clas, anchors, gt_boxes, gt_cats, cfg):
+        lib = _lib.load()
+        B, A, Cn = (int(v) for v in clas.shape)
+        M = int(gt_cats.shape[1])
+        dev = clas.device
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        H, W, base, K, table, _ = anchor_args(anchors)
+        world, group = cfg["world_size"], cfg["group"]
+        B_global = cfg["global_batch"] if cfg["global_batch"] else B * world
+        with torch.cuda.device(dev):
+            matches, npos, _ = assign_batch(anchors, gt_boxes, gt_cats, cfg["pos_thresh"], cfg["neg_thresh"])
+            dclas = torch.empty_like(clas) if need_grad else None
+            dreg = torch.empty_like(reg) if need_grad else None
+            out3 = torch.empty(3, dtype=torch.float32, device=dev)
+            ws = _ws.get(lib.rn_loss_workspace_bytes(B, A, Cn), dev)
+            _lib.check(lib.rn_loss(_lib.ptr(clas), _lib.ptr(reg), _lib.ptr(gt_boxes), _lib.ptr(gt_cats),
+                                   _lib.ptr(matches), _lib.ptr(npos), B, A, Cn, M, H, W, base, K, table,
+                                   float(cfg["alpha"]), float(cfg["gamma"]), float(cfg["beta"]), int(B_global),
+                                   _lib.ptr(dclas), _lib.ptr(dreg), _lib.ptr(out3), _lib.ptr(ws), ws.numel(),
+                                   _lib.stream_ptr(dev)))
+        if world > 1:
+            out3 = reduce_loss_scalars(out3, group)
+        ctx.grads = (dreg, dclas)
+        ctx.used = False
+        cfg["last_matches"], cfg["last_npos"] = matches, npos
+        loss, reg_loss, clas_loss = out3.unbind(0)
+        ctx.mark_non_differentiable(reg_loss, clas_loss)
+        return loss, reg_loss, clas_loss
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_reg, _g_clas):
+        dreg, dclas = ctx.grads
+        if dreg is None:
+            return None, None, None, None, None, None
+        if ctx.used:
+            raise RuntimeError("SSD_loss: backward through the same loss value twice is not supported; "
+                               "the gradients were produced (and scaled in place) by the first backward")
+        ctx.used = True
+        lib = _lib.load()
+        g = g_loss.detach().to(dtype=torch.float32).contiguous()
+        with torch.cuda.device(dclas.device):
+            _lib.check(lib.rn_scale_grads(_lib.ptr(dclas), dclas.numel(), _lib.ptr(dreg), dreg.numel(), _lib.ptr(g),
+                                          _lib.stream_ptr(dclas.device)))
+        return dreg, dclas, None, None, None, None
+
+
+def reduce_loss_scalars(out3, group=None):
+    """The one collective of the path: sums the three per-rank loss scalars over the image shards.
+    all_gather + a fixed rank-order sum (not all_reduce) so the result is bit-identical on every rank
+    and independent of the reduction algorithm NCCL picks."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(out3) for _ in range(world)]
+    dist.all_gather(parts, out3.contiguous(), group=group)
+    total = parts[0].clone()
+    for p in parts[1:]:
+        total += p
+    return total
+
+
+class SSD_loss(object):
+    """SSD / RetinaNet loss: (1-beta) * smooth-L1 + beta * focal (reference Vision.py:1607-1644).
+
+    Extra, optional arguments (the reference is single-GPU): `distributed=True` treats the batch given to
+    __call__ as this rank's image shard of a global batch of `global_batch` images (default: local batch x
+    world size): the kernels scale by 1/global_batch and the three scalars are summed over ranks with one
+    12-byte NCCL exchange; per-rank reg/clas gradients need no communication."""
+
+    def __init__(self, beta=0.5, alpha=0.25, gamma=2.0, distributed=False, process_group=None, global_batch=None):
+        self.beta, self.alpha, self.gamma = beta, alpha, gamma
+        self.distributed, self.process_group, self.global_batch = distributed, process_group, global_batch
+        self.pos_thresh, self.neg_thresh = 0.5, 0.4   # defaults of match_anchors_objects, Vision.py:1474
+        self.reg_loss = self.clas_loss = None
+        self._cfg = {}
+
+    def __call__(self, activ, target):
+        anchors, reg, clas = activ[0], activ[1], activ[2]
+        _lib.require_cuda(reg, "reg", torch.float32)
+        _lib.require_cuda(clas, "clas", torch.float32)
+        gt_boxes, gt_cats = _targets(target, clas.device)
+        if clas.dim() != 3 or reg.shape != clas.shape[:2] + (4,) or anchors.shape != (clas.shape[1], 4) \
+                or gt_cats.shape[0] != clas.shape[0]:
+            raise ValueError("expected anchors [A,4], reg [bs,A,4], clas [bs,A,C], targets of the same batch size")
+        world = 1
+        if self.distributed:
+            import torch.distributed as dist
+            world = dist.get_world_size(self.process_group)
+        cfg = dict(alpha=self.alpha, gamma=self.gamma, beta=self.beta, pos_thresh=self.pos_thresh,
+                   neg_thresh=self.neg_thresh, world_size=world, group=self.process_group,
+                   global_batch=self.global_batch)
+        loss, reg_loss, clas_loss = _SSDLossFunction.apply(reg.contiguous(), clas.contiguous(), anchors, gt_boxes,
+                                                           gt_cats, cfg)
+        self._cfg = cfg
+        self.reg_loss, self.clas_loss = reg_loss, clas_loss   # Vision.py:1643
+        return loss
+
+    @property
+    def last_assignment(self):
+        """(matches [bs,A] int32, npos [bs] int32) of the most recent call (device tensors)."""
+        return self._cfg.get("last_matches"), self._cfg.get("last_npos")
+
+
+class SSD_RegLoss(object):
+    """Metric that reads SSD_loss.reg_loss (reference Vision.py:1646-1654)."""
+
+    def __init__(self, loss_func):
+        self.loss_func = loss_func
+
+    def __call__(self, pred, target):
+        return self.loss_func.reg_loss
+
+
+class SSD_ClasLoss(object):
+    """Metric that reads SSD_loss.clas_loss (reference Vision.py:1656-1663)."""
+
+    def __init__(self, loss_func):
+        self.loss_func = loss_func
+
+    def __call__(self, pred, target):
+        return self.loss_func.clas_loss
+
+
+def match_anchors_objects(objects, anchors, pos_thresh=0.5, neg_thresh=0.4):
+    """Single-image assignment with the reference's return convention (Vision.py:1474-1511):
+    pos_idxs, neg_idxs (int64, ascending) and matches [N] int64 with -1 for every non-positive anchor.
+    `objects` is an (m x 4) tensor of real (non-padding) boxes."""
+    _lib.require_cuda(anchors, "anchors", torch.float32)
+    objects = torch.as_tensor(objects).to(device=anchors.device, dtype=torch.float32).reshape(-1, 4).contiguous()
+    m = int(objects.shape[0])
+    gt_boxes = objects.unsqueeze(0) if m else torch.zeros((1, 1, 4), dtype=torch.float32, device=anchors.device)
+    gt_cats = torch.zeros((1, max(m, 1)), dtype=torch.int64, device=anchors.device)
+    if m == 0:
+        gt_cats -= 1
+    mt, _, _ = assign_batch(anchors, gt_boxes.contiguous(), gt_cats, pos_thresh, neg_thresh)
+    mt = mt[0].long()
+    pos_idxs = (mt >= 0).nonzero().view(-1)
+    neg_idxs = (mt == _lib.MATCH_NEG).nonzero().view(-1)
+    return pos_idxs, neg_idxs, torch.where(mt >= 0, mt, torch.full_like(mt, -1))
+
+
+class ComputeMaxOverlaps(object):
+    """Mean over images of the mean over objects of each object's best IoU with any anchor (reference
+    Vision.py:1666-1694); all per-object values are appended to self.max_overlaps."""
+
+    def __init__(self):
+        self.max_overlaps = []
+
+    def __call__(self, activ, target):
+        lib = _lib.load()
+        anchors = activ[0]
+        gt_boxes, gt_cats = _targets(target, anchors.device)
+        B, M = int(gt_cats.shape[0]), int(gt_cats.shape[1])
+        H, W, base, K, table, A = anchor_args(anchors)
+        out = torch.empty((B, M), dtype=torch.float32, device=gt_boxes.device)
+        with torch.cuda.device(out.device):
+            _lib.check(lib.rn_max_overlaps(_lib.ptr(gt_boxes), _lib.ptr(gt_cats), B, M, H, W, base, K, table, A,
+                                           _lib.ptr(out), _lib.stream_ptr(out.device)))
+        host, valid = ARR(out), ARR(gt_cats) >= 0
+        means = []
+        for i in range(B):
+            v = host[i][valid[i]]
+            if len(v) == 0:
+                continue
+            self.max_overlaps += list(v)
+            means.append(v.mean())
+        return TEN(float(np.array(means).mean()) if means else 0.0)
