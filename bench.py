@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""Benchmark of the RetinaNet loss / post-processing hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches N ranks)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port, host cores)
+
+A "step" is one pass of the hot path over one synthetic COCO-shaped batch per GPU: anchor assignment +
+focal / smooth-L1 loss forward AND backward (SSD_loss(...) then loss.backward()), B=16 images of
+800x1344 (A = 201 600 anchors, 80 classes, M = 20 ground-truth slots) per GPU -- BASELINE.json
+configs[2].  Scaling is weak (per-GPU batch fixed); images shard over ranks with one 12-byte exchange of
+the loss scalars per step.  One JSON line is printed by rank 0.
+
+  value     images/s, inputs resident in HBM, through the public drop-in API (SSD_loss + backward)
+  e2e       same API, but every step first copies that step's inputs from pinned host memory and ends
+            with a device->host read of the loss
+  roofline  the streaming loss kernel: algorithmic bytes 8*A*(C+4) per image / CUDA-event time of the
+            rn_loss call measured inside the timed region, against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (a port of the reference's algorithm) on this box's host cores
+Extra keys `postproc` and `pascal` report BASELINE.json configs[3] / configs[1] the same way.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+COCO = dict(H=800, W=1344, C=80, M=20)
+PASCAL = dict(H=512, W=512, C=20, M=10)
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# synthetic inputs
+# --------------------------------------------------------------------------------------------------
+def device_activations(B, A, C, seed, device, mu):
+    """clas = sigmoid(N(mu,1)) and reg ~ N(0,0.25) generated on the device."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    clas = torch.empty((B, A, C), dtype=torch.float32, device=device)
+    for i in range(B):  # per image to bound the temporaries
+        clas[i] = torch.sigmoid(torch.randn((A, C), generator=g, device=device) + mu)
+    reg = torch.randn((B, A, 4), generator=g, device=device) * 0.5
+    return clas, reg
+
+
+def loss_bytes(B, A, C, grad=True):
+    return (8 if grad else 4) * A * (C + 4) * B
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def time_loss(cfg, B, steps, warmup, device, world, nbuf=2, seed=1002, with_events=True):
+    """Times `steps` loss fwd+bwd steps through SSD_loss; returns (ms_total, ms_loss_kernel_avg, launches)."""
+    import torch
+    import torch.distributed as dist
+
+    from neuralnetworklibrary_b200 import _lib, testing as syn
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator
+    from neuralnetworklibrary_b200.vision import SSD_loss
+
+    H, W, C, M = cfg["H"], cfg["W"], cfg["C"], cfg["M"]
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=device))
+    A = anchors.shape[0]
+    sets = []
+    for k in range(nbuf):
+        clas, reg = device_activations(B, A, C, seed + 17 * k, device, mu=-4.6)
+        gb, gc = syn.make_targets(B, M, H, W, C, seed=seed + 17 * k)
+        sets.append((clas.requires_grad_(True), reg.requires_grad_(True), gb.to(device), gc.to(device)))
+    loss_fn = SSD_loss(distributed=world > 1)
+
+    # CUDA-event timing of the rn_loss library call alone (dominant kernel + its tiny final reduction)
+    lib = _lib.load()
+    ev = []
+    orig = lib.rn_loss
+    if with_events:
+        def timed_rn_loss(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = orig(*a)
+            e1.record()
+            ev.append((e0, e1))
+            return rc
+        lib.rn_loss = timed_rn_loss
+
+    def step(k):
+        clas, reg, gb, gc = sets[k % nbuf]
+        clas.grad = None
+        reg.grad = None
+        loss = loss_fn([anchors, reg, clas], [gb, gc])
+        loss.backward()
+        return loss
+
+    try:
+        for k in range(warmup):
+            step(k)
+        del ev[:]
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for k in range(steps):
+            last = step(warmup + k)
+        t1.record()
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+    finally:
+        if with_events:
+            lib.rn_loss = orig
+    total_ms = t0.elapsed_time(t1)
+    kern_ms = statistics.mean(a.elapsed_time(b) for a, b in ev) if ev else None
+    if world > 1:
+        t = torch.tensor([total_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    # kernels per step: rn_assign(1) + rn_loss(2) + rn_scale_grads(1); the npos memset is not a kernel
+    return total_ms, kern_ms, 4 * steps, float(last.item()), A
+
+
+def time_loss_e2e(cfg, B, steps, warmup, device, world, seed=1002):
+    """Same step, but inputs start in pinned host memory every step and the loss is read back."""
+    import torch
+    import torch.distributed as dist
+
+    from neuralnetworklibrary_b200 import testing as syn
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator
+    from neuralnetworklibrary_b200.vision import SSD_loss
+
+    H, W, C, M = cfg["H"], cfg["W"], cfg["C"], cfg["M"]
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=device))
+    A = anchors.shape[0]
+    clas_d, reg_d = device_activations(B, A, C, seed, device, mu=-4.6)
+    gb, gc = syn.make_targets(B, M, H, W, C, seed=seed)
+    h_clas = torch.empty(clas_d.shape, dtype=torch.float32, pin_memory=True).copy_(clas_d)
+    h_reg = torch.empty(reg_d.shape, dtype=torch.float32, pin_memory=True).copy_(reg_d)
+    h_gb, h_gc = gb.pin_memory(), gc.pin_memory()
+    loss_fn = SSD_loss(distributed=world > 1)
+    h2d = h_clas.numel() * 4 + h_reg.numel() * 4 + h_gb.numel() * 4 + h_gc.numel() * 8
+    out = []
+
+    def step():
+        clas_d.requires_grad_(False).copy_(h_clas, non_blocking=True)
+        reg_d.requires_grad_(False).copy_(h_reg, non_blocking=True)
+        g1, g2 = h_gb.to(device, non_blocking=True), h_gc.to(device, non_blocking=True)
+        clas_d.grad = None
+        reg_d.grad = None
+        loss = loss_fn([anchors, reg_d.requires_grad_(True), clas_d.requires_grad_(True)], [g1, g2])
+        loss.backward()
+        out.append(loss.item())  # device -> host read of the step's result
+
+    for _ in range(max(1, min(warmup, 2))):
+        step()
+    torch.cuda.synchronize(device)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize(device)
+    ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, h2d, 4
+
+
+def time_postproc(cfg, B, steps, warmup, device, seed=1004):
+    """BASELINE.json configs[3]: decode + clip + threshold + top-k + NMS over a COCO-shaped batch."""
+    import torch
+
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator, BBoxPredictor
+
+    H, W, C = cfg["H"], cfg["W"], cfg["C"]
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=device))
+    A = anchors.shape[0]
+    clas, reg = device_activations(B, A, C, seed, device, mu=-6.0)
+    bp = BBoxPredictor()
+    # e2e-ish public call (includes the result copy to the host); and the device-only time by events
+    for _ in range(warmup):
+        out = bp.predict_arrays(H, W, reg, clas, anchors)
+    torch.cuda.synchronize(device)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    t0.record()
+    for _ in range(steps):
+        out = bp.predict_arrays(H, W, reg, clas, anchors)
+    t1.record()
+    torch.cuda.synchronize(device)
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    return t0.elapsed_time(t1), wall_ms, int(out["n_candidates"].mean()), int(out["counts"].sum()), A
+
+
+def cpu_baseline_loss(cfg, max_images=None):
+    """The CPU oracle on a bounded sample of the same workload (one image per host thread)."""
+    import numpy as np
+
+    from neuralnetworklibrary_b200 import testing as syn
+    from oracle import oracle as orc
+
+    H, W, C, M = cfg["H"], cfg["W"], cfg["C"], cfg["M"]
+    threads = orc.num_threads()
+    n = max(2, min(threads, max_images or 32))
+    an = orc.anchors(H, W)
+    A = an.shape[0]
+    rng = np.random.default_rng(1002)
+    clas = (1.0 / (1.0 + np.exp(-(rng.standard_normal((n, A, C), dtype=np.float32) - np.float32(4.6))))).astype(np.float32)
+    reg = rng.standard_normal((n, A, 4), dtype=np.float32) * np.float32(0.5)
+    gb, gc = syn.make_targets(n, M, H, W, C, seed=1002)
+    orc.loss(an[:1024], clas[:1, :1024], reg[:1, :1024], gb.numpy()[:1], gc.numpy()[:1])  # warm the library
+    t0 = time.perf_counter()
+    orc.loss(an, clas, reg, gb.numpy(), gc.numpy())
+    dt = time.perf_counter() - t0
+    return n / dt, min(threads, n), "oracle port, %d COCO-shaped images (800x1344, C=80) fwd+bwd, 1 image per thread, %.1f s" % (n, dt)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    B = args.per_gpu_batch
+    peak, peak_src = peaks()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms, kern_ms, launches, last_loss, A = time_loss(COCO, B, args.steps, args.warmup, device, world)
+    clocks = sampler.stop() if rank == 0 else None
+    images = B * world * args.steps
+    value = images / (total_ms * 1e-3)
+
+    e2e_ms, h2d, d2h = time_loss_e2e(COCO, B, max(2, min(args.steps, 5)), args.warmup, device, world)
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_value = B * world * e2e_steps / (e2e_ms * 1e-3)
+
+    line = None
+    if rank == 0:
+        alg = loss_bytes(B, A, COCO["C"])
+        achieved = alg / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "images/sec loss fwd+bwd (COCO shape)", "value": round(value, 1), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "coco_loss_fwd_bwd: assign + focal/smooth-L1 fwd+bwd, B=%d/GPU, 800x1344, A=%d, C=80, M=20"
+                                   % (B, A), "global_batch": B * world, "parallelism": "image-sharded dp%d" % world,
+                       "l2": "inputs (1.1 GB/step, 2 rotating sets) larger than the 126 MB L2", "api": "SSD_loss()+backward()"},
+            "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": None, "kernel": "rn_loss_kernel<4,20,true,true>",
+                         "kernel_ms": round(kern_ms, 4), "algorithmic_bytes": alg, "peak_source": peak_src},
+            "clocks": clocks, "loss": last_loss,
+        }
+        # extra workloads (device-timed, single GPU share of the job): post-processing and Pascal loss
+        try:
+            pms, pwall, ncand, nkept, _ = time_postproc(COCO, args.postproc_batch, max(3, args.steps // 2), 3, device)
+            psteps = max(3, args.steps // 2)
+            palg = loss_bytes(args.postproc_batch, A, COCO["C"], grad=False)
+            line["postproc"] = {"workload": "coco_postproc B=%d 800x1344 C=80 thresh=0.05 top_k=1000 max_boxes=20" % args.postproc_batch,
+                                "images_per_s": round(args.postproc_batch * psteps / (pms * 1e-3), 1),
+                                "images_per_s_e2e_wall": round(args.postproc_batch * psteps / (pwall * 1e-3), 1),
+                                "ms_per_step": round(pms / psteps, 4), "candidates_per_image": ncand, "kept": nkept,
+                                "roofline_frac_whole_call": round(palg / (pms / psteps * 1e-3) / 1e9 / peak, 4)}
+        except Exception as exc:  # keep the headline line even if an extra fails
+            line["postproc"] = {"error": repr(exc)}
+        try:
+            pt, pk, _, _, pA = time_loss(PASCAL, 32, args.steps, args.warmup, device, 1, nbuf=4, seed=1003)
+            line["pascal"] = {"workload": "pascal_loss_fwd_bwd B=32 512x512 C=20 M=10",
+                              "images_per_s": round(32 * args.steps / (pt * 1e-3), 1), "ms_per_step": round(pt / args.steps, 4),
+                              "rn_loss_ms": round(pk, 4),
+                              "roofline_frac_rn_loss": round(loss_bytes(32, pA, 20) / (pk * 1e-3) / 1e9 / peak, 4)}
+        except Exception as exc:
+            line["pascal"] = {"error": repr(exc)}
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_baseline_loss(COCO)
+            line["cpu_baseline"] = {"value": round(v, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's algorithm on the host cores (oracle port; the reference is Python and
+# /root/reference does not exist on the GPU box)
+# --------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return None
+    import numpy as np
+
+    from neuralnetworklibrary_b200 import testing as syn
+    from oracle import oracle as orc
+
+    orc.build()
+    H, W, C, M = COCO["H"], COCO["W"], COCO["C"], COCO["M"]
+    threads = orc.num_threads()
+    n = max(2, min(threads, 32))  # one step = a bounded sample: one COCO-shaped image per host thread
+    an = orc.anchors(H, W)
+    A = an.shape[0]
+    rng = np.random.default_rng(1002)
+    clas = (1.0 / (1.0 + np.exp(-(rng.standard_normal((n, A, C), dtype=np.float32) - np.float32(4.6))))).astype(np.float32)
+    reg = rng.standard_normal((n, A, 4), dtype=np.float32) * np.float32(0.5)
+    gb, gc = syn.make_targets(n, M, H, W, C, seed=1002)
+    gbn, gcn = gb.numpy(), gc.numpy()
+    for _ in range(min(args.warmup, 1)):
+        orc.loss(an, clas, reg, gbn, gcn)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.loss(an, clas, reg, gbn, gcn)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = "%d COCO-shaped images (800x1344, A=%d, C=80, M=20) per step, 1 image per thread" % (n, A)
+    line = {
+        "impl": "reference", "metric": "images/sec loss fwd+bwd (COCO shape)", "value": round(value, 3), "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "coco_loss_fwd_bwd: assign + focal/smooth-L1 fwd+bwd, 800x1344, A=%d, C=80, M=20" % A,
+                   "note": "reference algorithm on host cores (C port in oracle/; the reference itself is Python and is "
+                           "not present on the GPU box); bounded sample per step"},
+        "cpu_baseline": {"value": round(value, 3), "unit": "images/s", "cores": min(threads, n), "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--per-gpu-batch", type=int, default=16)
+    ap.add_argument("--postproc-batch", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,3 +90,52 @@ def make_infer_activations(B, A, C, seed, anchors=None, mu=-6.0, clusters=20, pe
             dup = (srt[1:] == srt[:-1]).nonzero().view(-1)
             tries += 1
     return clas, reg
+
+
+# --------------------------------------------------------------------------------------------------
+# Comparison helpers shared by tests/, smoke() and bench.py (tolerances: BASELINE.json north_star)
+# --------------------------------------------------------------------------------------------------
+RTOL = 1e-5
+
+
+def assert_rel(actual, expected, rtol=RTOL, what=""):
+    """Element-wise |a-e| <= rtol*|e| with NO absolute slack, and identical zero patterns."""
+    import numpy as np
+    actual, expected = np.asarray(actual), np.asarray(expected)
+    assert actual.shape == expected.shape, (what, actual.shape, expected.shape)
+    assert np.array_equal(actual == 0, expected == 0), what + ": zero patterns differ"
+    nz = expected != 0
+    if nz.any():
+        err = np.abs(actual[nz].astype(np.float64) - expected[nz]) / np.abs(expected[nz])
+        assert err.max() <= rtol, "%s: max rel err %.3g" % (what, err.max())
+
+
+def assert_dreg_close(actual, expected, rtol=RTOL, what="dreg"):
+    """Smooth-L1 gradients.  Below the knee the gradient is 9*(t-p)*g_e, i.e. proportional to a
+    DIFFERENCE of the encoded target t (which contains logf) and the prediction; one ulp of logf
+    (CUDA's vs the host libm's) therefore moves a near-zero element by up to ~2e-6*g_e no matter how
+    small the element is.  So: identical zero pattern, and |a-e| <= rtol*|e| + rtol*g_e, where
+    g_e = max|e| of the image is the gradient of any element above the knee."""
+    import numpy as np
+    actual, expected = np.asarray(actual), np.asarray(expected)
+    assert actual.shape == expected.shape
+    assert np.array_equal(actual == 0, expected == 0), what + ": zero patterns differ"
+    for i in range(expected.shape[0]):
+        scale = np.abs(expected[i]).max()
+        err = np.abs(actual[i].astype(np.float64) - expected[i])
+        bound = rtol * np.abs(expected[i]) + rtol * scale
+        assert (err <= bound).all(), "%s image %d: max excess %.3g (scale %.3g)" % (what, i, (err - bound).max(), scale)
+
+
+def assert_boxes_close(actual, expected, rtol=RTOL, what="boxes"):
+    """Decoded boxes [n,4]: |a-e| <= rtol * (largest |coordinate| of that box).  A coordinate is a
+    difference centre -/+ size/2 with size = w*expf(.), so its error scales with the box, not with the
+    coordinate itself (a corner near the image origin has no meaningful relative error)."""
+    import numpy as np
+    actual, expected = np.asarray(actual), np.asarray(expected)
+    assert actual.shape == expected.shape
+    if expected.size == 0:
+        return
+    scale = np.abs(expected).max(axis=-1, keepdims=True)
+    err = np.abs(actual.astype(np.float64) - expected)
+    assert (err <= rtol * np.maximum(scale, 1e-30)).all(), "%s: max err/scale %.3g" % (what, (err / np.maximum(scale, 1e-30)).max())

@@ -18,14 +18,8 @@ def dev():
     return torch.device("cuda:0")
 
 
-def rel_check(actual, expected, rtol=RTOL):
-    actual, expected = np.asarray(actual), np.asarray(expected)
-    assert actual.shape == expected.shape
-    assert np.array_equal(actual == 0, expected == 0), "zero patterns differ"
-    nz = expected != 0
-    if nz.any():
-        err = np.abs(actual[nz].astype(np.float64) - expected[nz]) / np.abs(expected[nz])
-        assert err.max() <= rtol, "max rel err %.3g" % err.max()
+rel_check = syn.assert_rel
+dreg_check = syn.assert_dreg_close
 
 
 def make_anchors(H, W, table_mode=False):
@@ -174,7 +168,7 @@ def test_loss_forward_backward(seed, H, W, C, B, M, kw, table_mode):
     assert np.array_equal(matches, o["matches"]) and np.array_equal(npos, o["npos"])
     np.testing.assert_allclose(out3, o["out3"], rtol=RTOL, atol=0)
     rel_check(dclas, o["dclas"])
-    rel_check(dreg, o["dreg"])
+    dreg_check(dreg, o["dreg"])
 
 
 def test_loss_golden_small(golden_dir):
@@ -186,7 +180,7 @@ def test_loss_golden_small(golden_dir):
         assert np.array_equal(matches, g["matches"])
         np.testing.assert_allclose(out3, g[variant + "_out3"], rtol=RTOL, atol=0)
         rel_check(dclas, g[variant + "_dclas"])
-        rel_check(dreg, g[variant + "_dreg"])
+        dreg_check(dreg, g[variant + "_dreg"])
 
 
 def test_loss_upstream_gradient_and_no_grad():
@@ -246,4 +240,4 @@ def test_loss_full_size(H, W, C, B, M, seed):
     assert np.array_equal(matches, o["matches"]) and np.array_equal(npos, o["npos"])
     np.testing.assert_allclose(out3, o["out3"], rtol=RTOL, atol=0)
     rel_check(dclas, o["dclas"])
-    rel_check(dreg, o["dreg"])
+    dreg_check(dreg, o["dreg"])

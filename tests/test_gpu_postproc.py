@@ -31,7 +31,7 @@ def compare(out, po):
         assert np.array_equal(out["anchor_idx"][i, :n], po["anchor_idx"][i, :n]), "keep indices differ (image %d)" % i
         assert np.array_equal(out["classes"][i, :n], po["classes"][i, :n])
         assert np.array_equal(out["scores"][i, :n], po["scores"][i, :n])
-        np.testing.assert_allclose(out["boxes"][i, :n], po["boxes"][i, :n], rtol=RTOL, atol=0)
+        syn.assert_boxes_close(out["boxes"][i, :n], po["boxes"][i, :n])
 
 
 POST_CASES = [  # seed, H, W, C, B, mu, kwargs
@@ -83,7 +83,7 @@ def test_postproc_golden_lists(golden_dir):
             assert isinstance(PC[i][0], np.int64) and isinstance(CS[i][0], np.float32)
             assert np.array_equal(np.array(PC[i]), g[name + "_classes"][i, :n])
             assert np.array_equal(np.array(CS[i]), g[name + "_scores"][i, :n])
-            np.testing.assert_allclose(np.stack(PB[i]), g[name + "_boxes"][i, :n], rtol=RTOL, atol=0)
+            syn.assert_boxes_close(np.stack(PB[i]), g[name + "_boxes"][i, :n])
             _ = PB[i][0] * 0.5   # callers rescale boxes with list_mult (Learner.py:377-381)
 
 

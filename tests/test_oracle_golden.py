@@ -21,15 +21,7 @@ def _sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def assert_rel(actual, expected, rtol=RTOL):
-    """Element-wise relative check with NO absolute slack: exact zeros must be exact zeros."""
-    actual, expected = np.asarray(actual), np.asarray(expected)
-    assert actual.shape == expected.shape
-    assert np.array_equal(actual == 0, expected == 0), "zero patterns differ"
-    nz = expected != 0
-    if nz.any():
-        err = np.abs(actual[nz].astype(np.float64) - expected[nz]) / np.abs(expected[nz])
-        assert err.max() <= rtol, "max rel err %.3g" % err.max()
+assert_rel = syn.assert_rel
 
 
 def test_anchor_tables_bitwise(golden_dir):
