@@ -42,6 +42,14 @@ __device__ __forceinline__ float4 rn_ldg_stream(const float4 *p) {
                  : "l"(p));
     return v;
 }
+// Scheduling fence for a loaded value: an empty volatile asm that "modifies" the registers.  Volatile
+// asm statements keep their program order, so placing one of these per value AFTER a block of
+// rn_ldg_stream calls forces every load of the block to be issued before the first consumer (ptxas
+// otherwise interleaves consumers with later loads to save registers, leaving one or two requests in
+// flight per warp).
+__device__ __forceinline__ void rn_keep_live(float4 &v) {
+    asm volatile("" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w));
+}
 // Streaming 128-bit store (evict-first in L2: the gradient is not re-read by this library).
 __device__ __forceinline__ void rn_stg_stream(float4 *p, float4 v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
@@ -95,6 +103,30 @@ __device__ __forceinline__ float4 rn_gen_anchor(const RnGeom &g, const double *s
 
 __device__ __forceinline__ float4 rn_anchor(const RnGeom &g, const double *s_base, const float4 *table, int a) {
     return table ? __ldg(table + a) : rn_gen_anchor(g, s_base, a);
+}
+
+// Same anchor, but the base table is read straight from the kernel parameter (constant bank, indexed
+// load).  For kernels that need an anchor only for the rare positive rows and should not pay a
+// shared-memory staging prologue in every CTA.
+__device__ __forceinline__ float4 rn_anchor_from_param(const RnGeom &g, const float4 *table, int a) {
+    if (table) return __ldg(table + a);
+    int l = (a >= g.off[1]) + (a >= g.off[2]) + (a >= g.off[3]) + (a >= g.off[4]);
+    int local = a - g.off[l];
+    int cell = local / g.K;
+    int k = local - cell * g.K;
+    int gw = g.gw[l];
+    int iy = cell / gw;
+    int ix = cell - iy * gw;
+    double stride = (double)(8 << l);
+    double sx = __dmul_rn((double)ix + 0.5, stride);
+    double sy = __dmul_rn((double)iy + 0.5, stride);
+    const double *b = g.base + (l * RN_MAX_K + k) * 4;
+    float4 r;
+    r.x = __double2float_rn(__dadd_rn(b[0], sx));
+    r.y = __double2float_rn(__dadd_rn(b[1], sy));
+    r.z = __double2float_rn(__dadd_rn(b[2], sx));
+    r.w = __double2float_rn(__dadd_rn(b[3], sy));
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------

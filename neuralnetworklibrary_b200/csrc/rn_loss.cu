@@ -32,7 +32,8 @@ struct RnLossParams {
     float *dclas;
     float *dreg;
     float *partials;  // [B][tiles][2] : {sum of focal terms, sum of smooth-L1 terms}
-    int B, A, C, CV, M, tiles;
+    unsigned int *ticket;  // last-block election counter of the final kernel
+    int B, A, C, CV, M, tiles, iters;
     float a_pos, a_neg, gamma, lo, hi;
     float wc_over_bs, wr_over_bs;  // beta / B_global, (1-beta) / B_global   (Vision.py:1644)
 };
@@ -109,42 +110,24 @@ struct RnVec<1> {
     __device__ __forceinline__ float &at(int) { return d; }
 };
 
-// V: floats per vector (4 when C % 4 == 0, else 1).  CVT: compile-time vectors per row (0 = runtime).
-template <int V, int CVT, bool G2, bool GRAD>
-__global__ void __launch_bounds__(RN_THREADS)
-rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ RnGeom g) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    // layout: base doubles | gt boxes float4[M] | gt cats int[M]
-    double *s_base = reinterpret_cast<double *>(smem);
-    float4 *s_box = reinterpret_cast<float4 *>(smem + sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4);
-    int *s_cat = reinterpret_cast<int *>(s_box + P.M);
-    __shared__ float s_red[2][RN_THREADS / 32];
-
+// One sub-tile of RN_LOSS_TILE vectors: U independent 128-bit loads per thread are issued first, then
+// the element math, then the stores.  FULL = the sub-tile lies completely inside the image, so there is
+// no per-vector bounds predicate; addresses are one 64-bit base per thread plus immediates.
+template <int V, int CVT, bool G2, bool GRAD, bool FULL>
+__device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, const float *__restrict__ x_img,
+                                                float *__restrict__ dx_img, const int32_t *__restrict__ m_img,
+                                                const int *s_cat, int CV, int nvec, int tile0, float gl,
+                                                float &acc_neg, float &acc_pos) {
     const int tid = threadIdx.x;
-    const int b = blockIdx.y;
-    const int A = P.A;
-    const int CV = CVT ? CVT : P.CV;
-    const int nvec = A * CV;  // vectors in one image
-    const int tile0 = blockIdx.x * RN_LOSS_TILE;
-
-    if (!P.table) rn_stage_base(g, s_base);
-    if (tid < 32) rn_compact_gt(P.gt_boxes + (size_t)b * P.M, P.gt_cats + (size_t)b * P.M, P.M, s_box, nullptr, s_cat);
-
-    const int n_pos = P.npos[b];
-    const float n_norm = fmaxf((float)n_pos, 1.0f);                  // clamp(min=1), Vision.py:1530
-    const float gl = __fdiv_rn(P.wc_over_bs, n_norm);                // upstream of every focal term
-    const float *x_img = P.clas + (size_t)b * A * P.C;
-    float *dx_img = GRAD ? P.dclas + (size_t)b * A * P.C : nullptr;
-    const int32_t *m_img = P.matches + (size_t)b * A;
-
-    // ---- issue all loads of the tile first (U independent 128-bit loads per thread) ----
+    const int v0 = tile0 + tid;
+    const float *xp = x_img + (size_t)v0 * V;
     RnVec<V> xv[RN_LOSS_U];
     int mrow[RN_LOSS_U];
 #pragma unroll
     for (int u = 0; u < RN_LOSS_U; ++u) {
-        const int v = tile0 + u * RN_THREADS + tid;
-        if (v < nvec) {
-            xv[u].load(x_img + (size_t)v * V);
+        const int v = v0 + u * RN_THREADS;
+        if (FULL || v < nvec) {
+            xv[u].load(xp + (size_t)u * RN_THREADS * V);
             mrow[u] = __ldg(m_img + v / CV);
         } else {
             mrow[u] = RN_MATCH_IGNORE;
@@ -152,23 +135,22 @@ rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ R
             for (int e = 0; e < V; ++e) xv[u].at(e) = 0.5f;
         }
     }
-    __syncthreads();  // s_cat / s_box / s_base visible
-
-    float acc_neg = 0.0f, acc_pos = 0.0f;
+    float *dp = GRAD ? dx_img + (size_t)v0 * V : nullptr;
 #pragma unroll
     for (int u = 0; u < RN_LOSS_U; ++u) {
-        const int v = tile0 + u * RN_THREADS + tid;
         const int m = mrow[u];
         const float a_row = (m == RN_MATCH_IGNORE) ? 0.0f : P.a_neg;  // ignored anchors contribute nothing
         const float ga = a_row * gl;
-        int pe = -1;  // element of this vector that is the positive class, if any
-        if (m >= 0) {
-            const int row = v / CV;
-            pe = s_cat[m] - (v - row * CV) * V;  // Vision.py:1588-1593
-        }
         float part = 0.0f;
         RnVec<V> gv;
-        if ((unsigned)pe >= (unsigned)V) {  // common case: every element has target 0
+        bool slow = false;
+        int pe = -1;
+        if (m >= 0) {  // rare: a positive anchor; is its class inside this vector?  (Vision.py:1588-1593)
+            const int v = v0 + u * RN_THREADS;
+            pe = s_cat[m] - (v - (v / CV) * CV) * V;
+            slow = (unsigned)pe < (unsigned)V;
+        }
+        if (!slow) {  // common case: every element has target 0
 #pragma unroll
             for (int e = 0; e < V; ++e) gv.at(e) = rn_focal_elem<false, G2, GRAD>(xv[u].at(e), P.lo, P.hi, P.gamma, ga, part);
         } else {
@@ -184,14 +166,54 @@ rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ R
             }
         }
         acc_neg = fmaf(0.5f * a_row, part, acc_neg);
-        if (GRAD && v < nvec) gv.store(dx_img + (size_t)v * V);
+        if (GRAD && (FULL || v0 + u * RN_THREADS < nvec)) gv.store(dp + (size_t)u * RN_THREADS * V);
+    }
+}
+
+// V: floats per vector (4 when C % 4 == 0, else 1).  CVT: compile-time vectors per row (0 = runtime).
+// Each CTA handles P.iters consecutive sub-tiles of one image (the prologue -- ground-truth compaction,
+// per-image scalars -- and the block reduction are paid once per CTA).
+template <int V, int CVT, bool G2, bool GRAD>
+__global__ void __launch_bounds__(RN_THREADS)
+rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ RnGeom g) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    // layout: gt boxes float4[M] | gt cats int[M]
+    float4 *s_box = reinterpret_cast<float4 *>(smem);
+    int *s_cat = reinterpret_cast<int *>(s_box + P.M);
+    __shared__ float s_red[2][RN_THREADS / 32];
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int A = P.A;
+    const int CV = CVT ? CVT : P.CV;
+    const int nvec = A * CV;  // vectors in one image
+    const int cta0 = blockIdx.x * (RN_LOSS_TILE * P.iters);
+    const int cta1 = min(nvec, cta0 + RN_LOSS_TILE * P.iters);
+
+    if (tid < 32) rn_compact_gt(P.gt_boxes + (size_t)b * P.M, P.gt_cats + (size_t)b * P.M, P.M, s_box, nullptr, s_cat);
+
+    const int n_pos = P.npos[b];
+    const float n_norm = fmaxf((float)n_pos, 1.0f);    // clamp(min=1), Vision.py:1530
+    const float gl = __fdiv_rn(P.wc_over_bs, n_norm);  // upstream of every focal term
+    const float *x_img = P.clas + (size_t)b * A * P.C;
+    float *dx_img = GRAD ? P.dclas + (size_t)b * A * P.C : nullptr;
+    const int32_t *m_img = P.matches + (size_t)b * A;
+    __syncthreads();  // s_cat / s_box visible
+
+    float acc_neg = 0.0f, acc_pos = 0.0f;
+#pragma unroll 1
+    for (int tile0 = cta0; tile0 < cta1; tile0 += RN_LOSS_TILE) {
+        if (tile0 + RN_LOSS_TILE <= nvec)
+            rn_loss_subtile<V, CVT, G2, GRAD, true>(P, x_img, dx_img, m_img, s_cat, CV, nvec, tile0, gl, acc_neg, acc_pos);
+        else
+            rn_loss_subtile<V, CVT, G2, GRAD, false>(P, x_img, dx_img, m_img, s_cat, CV, nvec, tile0, gl, acc_neg, acc_pos);
     }
 
-    // ---- regression rows whose first vector lies in this tile: smooth L1 (Vision.py:1532-1566) ----
+    // ---- regression rows whose first vector lies in this CTA's range: smooth L1 (Vision.py:1532-1566) ----
     float acc_reg = 0.0f;
     {
-        const int r0 = (tile0 + CV - 1) / CV;
-        const int r1 = min(A, (tile0 + RN_LOSS_TILE + CV - 1) / CV);
+        const int r0 = (cta0 + CV - 1) / CV;
+        const int r1 = min(A, (cta1 + CV - 1) / CV);
         const float numel = (float)(4 * n_pos);
         const float ge = n_pos > 0 ? __fdiv_rn(P.wr_over_bs, numel) : 0.0f;  // mean() backward
         const float4 *reg4 = reinterpret_cast<const float4 *>(P.reg) + (size_t)b * A;
@@ -201,7 +223,7 @@ rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ R
             const int m = __ldg(m_img + row);
             float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (m >= 0) {
-                const float4 an = rn_anchor(g, s_base, P.table, row);
+                const float4 an = rn_anchor_from_param(g, P.table, row);
                 const float4 tg = s_box[m];
                 const float4 pr = __ldg(reg4 + row);
                 const float aw = __fsub_rn(an.z, an.x), ah = __fsub_rn(an.w, an.y);
@@ -253,42 +275,59 @@ rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ R
         }
         float2 *out = reinterpret_cast<float2 *>(P.partials) + ((size_t)b * P.tiles + blockIdx.x);
         *out = make_float2(cs, rs);
+        if (blockIdx.x == 0 && b == 0) *P.ticket = 0u;  // arms the final kernel's last-block election
     }
 }
 
-// One CTA: per image, sum the CTA partials in a fixed order in float64, normalise like the reference
-// (Vision.py:1530, :1566), accumulate over images in fp32 in image order (Vision.py:1640-1641) and
-// combine (Vision.py:1643-1644).
-__global__ void __launch_bounds__(1024)
+// One CTA per image: sums that image's CTA partials in a fixed order (float64), normalises like the
+// reference (Vision.py:1530, :1566).  The last CTA to finish (ticket counter, armed by the loss kernel)
+// accumulates over images in fp32 in image order (Vision.py:1640-1641) and combines (Vision.py:1643-1644).
+__global__ void __launch_bounds__(RN_THREADS)
 rn_loss_final_kernel(const float2 *__restrict__ partials, const int32_t *__restrict__ npos, int B, int tiles,
-                     float w_reg, float w_clas, float bs, float *__restrict__ per_image /*[B][2]*/,
+                     float w_reg, float w_clas, float bs, float *per_image /*[B][2]*/, unsigned int *ticket,
                      float *__restrict__ out3) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int b = warp; b < B; b += nwarps) {
-        double cs = 0.0, rs = 0.0;
-        for (int t = lane; t < tiles; t += 32) {
-            float2 p = partials[(size_t)b * tiles + t];
-            cs += (double)p.x;
-            rs += (double)p.y;
-        }
+    __shared__ double s_c[RN_THREADS / 32], s_r[RN_THREADS / 32];
+    __shared__ bool s_last;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    double cs = 0.0, rs = 0.0;
+    for (int t = tid; t < tiles; t += RN_THREADS) {
+        const float2 p = partials[(size_t)b * tiles + t];
+        cs += (double)p.x;
+        rs += (double)p.y;
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            cs += __shfl_xor_sync(RN_FULL_MASK, cs, o);
-            rs += __shfl_xor_sync(RN_FULL_MASK, rs, o);
-        }
-        if (lane == 0) {
-            const int n = npos[b];
-            const float n_norm = fmaxf((float)n, 1.0f);
-            per_image[2 * b + 0] = n > 0 ? __fdiv_rn((float)rs, (float)(4 * n)) : 0.0f;  // reg loss of image b
-            per_image[2 * b + 1] = __fdiv_rn((float)cs, n_norm);                          // clas loss of image b
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        cs += __shfl_xor_sync(RN_FULL_MASK, cs, o);
+        rs += __shfl_xor_sync(RN_FULL_MASK, rs, o);
+    }
+    if ((tid & 31) == 0) {
+        s_c[tid >> 5] = cs;
+        s_r[tid >> 5] = rs;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
+        cs = 0.0;
+        rs = 0.0;
+#pragma unroll
+        for (int w = 0; w < RN_THREADS / 32; ++w) {
+            cs += s_c[w];
+            rs += s_r[w];
+        }
+        const int n = npos[b];
+        const float n_norm = fmaxf((float)n, 1.0f);
+        per_image[2 * b + 0] = n > 0 ? __fdiv_rn((float)rs, (float)(4 * n)) : 0.0f;  // reg loss of image b
+        per_image[2 * b + 1] = __fdiv_rn((float)cs, n_norm);                          // clas loss of image b
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == (unsigned)(B - 1));
+    }
+    __syncthreads();
+    if (s_last && tid == 0) {
+        __threadfence();
+        const volatile float *pi = per_image;
         float reg_total = 0.f, clas_total = 0.f;
-        for (int b = 0; b < B; ++b) {
-            reg_total = __fadd_rn(reg_total, per_image[2 * b + 0]);
-            clas_total = __fadd_rn(clas_total, per_image[2 * b + 1]);
+        for (int i = 0; i < B; ++i) {
+            reg_total = __fadd_rn(reg_total, pi[2 * i + 0]);
+            clas_total = __fadd_rn(clas_total, pi[2 * i + 1]);
         }
         const float reg_loss = __fdiv_rn(reg_total, bs), clas_loss = __fdiv_rn(clas_total, bs);
         out3[0] = __fadd_rn(__fmul_rn(w_reg, reg_loss), __fmul_rn(w_clas, clas_loss));
@@ -323,17 +362,30 @@ rn_scale_kernel(float *__restrict__ a, size_t na, float *__restrict__ bptr, size
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
-static int rn_loss_tiles(int A, int C) {
+// Sub-tiles per CTA: as many as possible (amortises the CTA prologue / reduction) while the grid still
+// has >= ~8 waves of 148 SMs x 3 resident CTAs.
+static int rn_loss_iters(int B, int A, int C) {
     const int V = (C % 4 == 0) ? 4 : 1;
-    const long long nvec = (long long)A * (C / V);
-    return (int)((nvec + RN_LOSS_TILE - 1) / RN_LOSS_TILE);
+    const long long sub = ((long long)A * (C / V) + RN_LOSS_TILE - 1) / RN_LOSS_TILE;
+    int it = 4;
+    while (it > 1 && (long long)B * ((sub + it - 1) / it) < 8LL * 148 * 3) it >>= 1;
+    return it;
+}
+static int rn_loss_tiles(int B, int A, int C) {  // CTAs (= partials) per image
+    const int V = (C % 4 == 0) ? 4 : 1;
+    const long long sub = ((long long)A * (C / V) + RN_LOSS_TILE - 1) / RN_LOSS_TILE;
+    const int it = rn_loss_iters(B, A, C);
+    return (int)((sub + it - 1) / it);
 }
 
 extern "C" size_t rn_loss_workspace_bytes(int B, int A, int C) {
     if (B <= 0 || A <= 0 || C <= 0) return 256;
-    size_t partials = sizeof(float2) * (size_t)B * (size_t)rn_loss_tiles(A, C);
+    // worst case over the tiling choice (iters = 1), so the size does not depend on the heuristic
+    const int V = (C % 4 == 0) ? 4 : 1;
+    const size_t sub = (size_t)(((long long)A * (C / V) + RN_LOSS_TILE - 1) / RN_LOSS_TILE);
+    size_t partials = sizeof(float2) * (size_t)B * sub;
     size_t per_image = sizeof(float) * 2 * (size_t)B;
-    return ((partials + 255) / 256) * 256 + ((per_image + 255) / 256) * 256;
+    return ((partials + 255) / 256) * 256 + ((per_image + 255) / 256) * 256 + 256;
 }
 
 template <int V, int CVT>
@@ -368,14 +420,14 @@ extern "C" int rn_loss(const float *clas, const float *reg, const float *gt_boxe
     int rc = rn_build_geom(&g, H, W, base, K, anchors, A);
     if (rc) return rc;
 
-    const int tiles = rn_loss_tiles(A, C);
+    const int tiles = rn_loss_tiles(B, A, C);
     RnLossParams P;
     P.clas = clas; P.reg = reg;
     P.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); P.gt_cats = gt_cats;
     P.matches = matches; P.npos = npos; P.table = reinterpret_cast<const float4 *>(anchors);
     P.dclas = dclas; P.dreg = dreg;
     P.partials = reinterpret_cast<float *>(workspace);
-    P.B = B; P.A = A; P.C = C; P.CV = C / V; P.M = M; P.tiles = tiles;
+    P.B = B; P.A = A; P.C = C; P.CV = C / V; P.M = M; P.tiles = tiles; P.iters = rn_loss_iters(B, A, C);
     P.a_pos = (float)alpha; P.a_neg = (float)(1.0 - alpha);  // Vision.py:1526
     P.gamma = (float)gamma;
     P.lo = (float)1e-4; P.hi = (float)(1.0 - 1e-4);          // Vision.py:1524
@@ -383,10 +435,12 @@ extern "C" int rn_loss(const float *clas, const float *reg, const float *gt_boxe
     const float w_reg = (float)(1.0 - beta), w_clas = (float)beta;  // Vision.py:1644
     P.wc_over_bs = w_clas / bs;
     P.wr_over_bs = w_reg / bs;
-    float *per_image = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(workspace) +
-                                                 ((sizeof(float2) * (size_t)B * tiles + 255) / 256) * 256);
+    unsigned char *wsb = reinterpret_cast<unsigned char *>(workspace);
+    const size_t ws_total = rn_loss_workspace_bytes(B, A, C);
+    float *per_image = reinterpret_cast<float *>(wsb + ws_total - 256 - ((sizeof(float) * 2 * (size_t)B + 255) / 256) * 256);
+    P.ticket = reinterpret_cast<unsigned int *>(wsb + ws_total - 256);
 
-    const size_t smem = sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4 + (size_t)M * (sizeof(float4) + sizeof(int));
+    const size_t smem = (size_t)M * (sizeof(float4) + sizeof(int));
     if (smem > 48 * 1024) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: M=%d too large", M);
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(tiles, B);
@@ -397,8 +451,8 @@ extern "C" int rn_loss(const float *clas, const float *reg, const float *gt_boxe
     else rn_launch_loss<1, 0>(g2, grad, grid, smem, s, P, g);
     rc = rn_check_launch("rn_loss");
     if (rc) return rc;
-    rn_loss_final_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const float2 *>(P.partials), npos, B, tiles, w_reg,
-                                            w_clas, bs, per_image, out3);
+    rn_loss_final_kernel<<<B, RN_THREADS, 0, s>>>(reinterpret_cast<const float2 *>(P.partials), npos, B, tiles, w_reg,
+                                                  w_clas, bs, per_image, P.ticket, out3);
     return rn_check_launch("rn_loss_final");
 }
 

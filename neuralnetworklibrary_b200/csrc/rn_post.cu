@@ -61,78 +61,147 @@ __device__ __forceinline__ void rn_argmax_update(float v, int c, float &best, in
 // ------------------------------------------------------------------------------------------------
 // K3a
 // ------------------------------------------------------------------------------------------------
-#define RN_SCAN_STEPS 4
+#define RN_SCAN_ROWS 1024  // anchor rows per CTA
 
-// V = floats per load (4 or 1), L = lanes per anchor row (4 or 1).
-template <int V, int L>
+// Candidate key: [sortable score : 32][~anchor : 24][class : 8] when the anchor index fits 24 bits and
+// the class 8 bits (PACK), else [sortable score : 32][~anchor : 32] and the class is re-derived later.
+// Either way keys are unique and their descending order is (score desc, anchor asc).
+__device__ __forceinline__ unsigned long long rn_make_key(float score, int a, int cls, bool pack) {
+    const unsigned long long hi = (unsigned long long)rn_float_sortable(score) << 32;
+    if (pack) return hi | ((unsigned long long)(0xffffffu - (unsigned)a) << 8) | (unsigned long long)(cls & 0xff);
+    return hi | (unsigned long long)(0xffffffffu - (unsigned)a);
+}
+__device__ __forceinline__ int rn_key_anchor(unsigned long long key, bool pack) {
+    return pack ? (int)(0xffffffu - (unsigned)((key >> 8) & 0xffffffull)) : (int)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+}
+
+// V = floats per load (4 or 1); L = lanes per anchor row (4 or 1); NV = loads per lane per row when it
+// is a compile-time constant (C == V*L*NV), 0 = runtime loop; R = rows per lane group in flight.
+// All R*NV loads of a step are issued before the first compare, so every warp keeps R*NV independent
+// 128-bit requests in flight (the first version had a runtime-trip-count loop: one request in flight
+// per warp and 27 % of DRAM peak, profiles/r01_first_pass.md).
+template <int V, int L, int NV, int R>
 __global__ void __launch_bounds__(RN_THREADS)
 rn_post_scan_kernel(const float *__restrict__ clas, const float *__restrict__ reg, int C,
                     const __grid_constant__ RnGeom g, const float4 *__restrict__ table,
-                    const __grid_constant__ RnDecode dec, float thresh, unsigned long long *__restrict__ keys,
-                    int32_t *__restrict__ counts) {
+                    const __grid_constant__ RnDecode dec, float thresh, int pack,
+                    unsigned long long *__restrict__ keys, int32_t *__restrict__ counts) {
     extern __shared__ __align__(16) unsigned char smem[];
+    // layout: base doubles | candidate keys of this CTA [RN_SCAN_ROWS]
     double *s_base = reinterpret_cast<double *>(smem);
+    unsigned long long *s_keys = reinterpret_cast<unsigned long long *>(smem + sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4);
+    __shared__ int s_count, s_pos;
     if (!table) rn_stage_base(g, s_base);
+    if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
 
     const int b = blockIdx.y, A = g.A;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = lane % L;           // position inside the row group
-    const int rows_per_warp = 32 / L;
-    const int rows_per_cta = (RN_THREADS / 32) * rows_per_warp * RN_SCAN_STEPS;
+    const int sub = lane % L;  // position inside the row group
+    constexpr int GROUPS = 32 / L;
+    constexpr int ROWS_PER_WARP = GROUPS * R;
+    constexpr int STEPS = RN_SCAN_ROWS / ((RN_THREADS / 32) * ROWS_PER_WARP);
+    constexpr int ROWS_PER_CTA = RN_SCAN_ROWS;
     const int CV = C / V;
     const float *clas_b = clas + (size_t)b * A * C;
 
 #pragma unroll 1
-    for (int step = 0; step < RN_SCAN_STEPS; ++step) {
-        const int a = blockIdx.x * rows_per_cta + (step * (RN_THREADS / 32) + warp) * rows_per_warp + lane / L;
-        float best = -INFINITY;
-        int bc = 0;
-        if (a < A) {
-            const float *row = clas_b + (size_t)a * C;
-            if (V == 4) {
-                const float4 *row4 = reinterpret_cast<const float4 *>(row);
-#pragma unroll 5
-                for (int j = sub; j < CV; j += L) {
-                    const float4 x = (L == 1) ? __ldg(row4 + j) : rn_ldg_stream(row4 + j);
-                    rn_argmax_update(x.x, 4 * j + 0, best, bc);
-                    rn_argmax_update(x.y, 4 * j + 1, best, bc);
-                    rn_argmax_update(x.z, 4 * j + 2, best, bc);
-                    rn_argmax_update(x.w, 4 * j + 3, best, bc);
-                }
-            } else {
-                for (int j = sub; j < CV; j += L) rn_argmax_update(__ldg(row + j), j, best, bc);
-            }
-        }
-        if (L > 1) {  // combine the L lanes of a row: larger value, then lower class index
+    for (int step = 0; step < STEPS; ++step) {
+        const int a0 = blockIdx.x * ROWS_PER_CTA + (step * (RN_THREADS / 32) + warp) * ROWS_PER_WARP + lane / L;
+        float best[R];
+        int bc[R];
+        if (NV > 0 && V == 4) {
+            float4 x[R][NV > 0 ? NV : 1];
 #pragma unroll
-            for (int o = L / 2; o > 0; o >>= 1) {
-                const float ov = __shfl_xor_sync(RN_FULL_MASK, best, o);
-                const int oc = __shfl_xor_sync(RN_FULL_MASK, bc, o);
-                if (ov > best || (ov == best && oc < bc)) {
-                    best = ov;
-                    bc = oc;
+            for (int r = 0; r < R; ++r) {
+                const int a = a0 + r * GROUPS;
+                const float4 *row4 = reinterpret_cast<const float4 *>(clas_b + (size_t)min(a, A - 1) * C);
+#pragma unroll
+                for (int j = 0; j < NV; ++j) x[r][j] = (L == 1) ? __ldg(row4 + sub + j * L) : rn_ldg_stream(row4 + sub + j * L);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) rn_keep_live(x[r][j]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                best[r] = -INFINITY;
+                bc[r] = 0;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    const int c0 = 4 * (sub + j * L);
+                    rn_argmax_update(x[r][j].x, c0 + 0, best[r], bc[r]);
+                    rn_argmax_update(x[r][j].y, c0 + 1, best[r], bc[r]);
+                    rn_argmax_update(x[r][j].z, c0 + 2, best[r], bc[r]);
+                    rn_argmax_update(x[r][j].w, c0 + 3, best[r], bc[r]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int a = a0 + r * GROUPS;
+                best[r] = -INFINITY;
+                bc[r] = 0;
+                if (a < A) {
+                    const float *row = clas_b + (size_t)a * C;
+                    if (V == 4) {
+                        const float4 *row4 = reinterpret_cast<const float4 *>(row);
+#pragma unroll 4
+                        for (int j = sub; j < CV; j += L) {
+                            const float4 xx = __ldg(row4 + j);
+                            rn_argmax_update(xx.x, 4 * j + 0, best[r], bc[r]);
+                            rn_argmax_update(xx.y, 4 * j + 1, best[r], bc[r]);
+                            rn_argmax_update(xx.z, 4 * j + 2, best[r], bc[r]);
+                            rn_argmax_update(xx.w, 4 * j + 3, best[r], bc[r]);
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int j = sub; j < CV; j += L) rn_argmax_update(__ldg(row + j), j, best[r], bc[r]);
+                    }
                 }
             }
         }
-        bool ok = (a < A) && (sub == 0) && (best > thresh);  // strict, retinanet.py:760
-        if (ok) {
-            const float4 an = rn_anchor(g, s_base, table, a);
-            const float4 rg = __ldg(reinterpret_cast<const float4 *>(reg) + (size_t)b * A + a);
-            ok = rn_box_nonempty(rn_decode(an, rg, dec));
-        }
-        const unsigned m = __ballot_sync(RN_FULL_MASK, ok);
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            int basepos = 0;
-            if (lane == leader) basepos = atomicAdd(counts + b, __popc(m));
-            basepos = __shfl_sync(RN_FULL_MASK, basepos, leader);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int a = a0 + r * GROUPS;
+            if (L > 1) {  // combine the L lanes of a row: larger value, then lower class index
+#pragma unroll
+                for (int o = L / 2; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(RN_FULL_MASK, best[r], o);
+                    const int oc = __shfl_xor_sync(RN_FULL_MASK, bc[r], o);
+                    if (ov > best[r] || (ov == best[r] && oc < bc[r])) {
+                        best[r] = ov;
+                        bc[r] = oc;
+                    }
+                }
+            }
+            bool ok = (a < A) && (sub == 0) && (best[r] > thresh);  // strict, retinanet.py:760
             if (ok) {
-                const int pos = basepos + __popc(m & ((1u << lane) - 1u));
-                keys[(size_t)b * A + pos] =
-                    ((unsigned long long)rn_float_sortable(best) << 32) | (unsigned long long)(0xffffffffu - (unsigned)a);
+                const float4 an = rn_anchor(g, s_base, table, a);
+                const float4 rg = __ldg(reinterpret_cast<const float4 *>(reg) + (size_t)b * A + a);
+                ok = rn_box_nonempty(rn_decode(an, rg, dec));
+            }
+            // candidates are collected per CTA in shared memory (one shared atomic per warp) ...
+            const unsigned m = __ballot_sync(RN_FULL_MASK, ok);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int basepos = 0;
+                if (lane == leader) basepos = atomicAdd(&s_count, __popc(m));
+                basepos = __shfl_sync(RN_FULL_MASK, basepos, leader);
+                if (ok) s_keys[basepos + __popc(m & ((1u << lane) - 1u))] = rn_make_key(best[r], a, bc[r], pack != 0);
             }
         }
+    }
+    // ... and appended to the image's list with ONE global atomic per CTA (per-warp global atomics on a
+    // single per-image counter serialised in L2 and held the first version to 27 % of DRAM peak).
+    __syncthreads();
+    const int n = s_count;
+    if (threadIdx.x == 0 && n > 0) s_pos = atomicAdd(counts + b, n);
+    __syncthreads();
+    if (n > 0) {
+        unsigned long long *dst = keys + (size_t)b * A + s_pos;
+        for (int i = threadIdx.x; i < n; i += RN_THREADS) dst[i] = s_keys[i];
     }
 }
 
@@ -140,7 +209,7 @@ rn_post_scan_kernel(const float *__restrict__ clas, const float *__restrict__ re
 __global__ void rn_make_keys_kernel(const float *__restrict__ scores, int n, unsigned long long *__restrict__ keys,
                                     int32_t *__restrict__ count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = ((unsigned long long)rn_float_sortable(scores[i]) << 32) | (unsigned long long)(0xffffffffu - (unsigned)i);
+    if (i < n) keys[i] = rn_make_key(scores[i], i, 0, false);
     if (i == 0) *count = n;
 }
 
@@ -188,8 +257,12 @@ rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t
     if (tid == 0) nsel[b] = K;
     if (K == 0) return;
 
+    // Sort as few keys as possible: the radix passes narrow the candidates down to `limit` keys (a
+    // power of two >= K), so the bitonic network is sized by top_k, not by the candidate count.
+    int limit = 1024;
+    while (limit < K) limit <<= 1;
     int total;  // keys staged in s_keys
-    if (n <= RN_SORT_N) {
+    if (n <= limit) {
         for (int i = tid; i < n; i += RN_SEL_THREADS) s_keys[i] = kb[i];
         total = n;
     } else {
@@ -222,7 +295,7 @@ rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t
             done += db;
             const int bincnt = s_bincnt;
             __syncthreads();
-            if (above_total + bincnt <= RN_SORT_N || done == 64) break;
+            if (above_total + bincnt <= limit || done == 64) break;
         }
         if (tid == 0) s_n = 0;
         __syncthreads();
@@ -261,20 +334,19 @@ rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3c: gather + bitmask NMS + sweep
+// K3c: gather + class-aware greedy NMS in rank chunks of 64 (bitmask form)
 // ------------------------------------------------------------------------------------------------
 struct RnNmsParams {
     const unsigned long long *sel;  // [B][top_k] sorted keys
     const int32_t *nsel;            // [B]
-    unsigned long long *mask;       // [B][top_k][words]
     // FROM_BOXES = false: re-derive from the activations
     const float *clas, *reg;
     const float4 *table;
-    int A, C;
+    int A, C, pack;
     // FROM_BOXES = true
     const float4 *boxes_in;
     const int64_t *classes_in;
-    int top_k, words, max_keep;
+    int top_k, max_keep;
     float max_overlap;
     // outputs (each may be NULL)
     float4 *out_boxes;
@@ -284,6 +356,13 @@ struct RnNmsParams {
     int32_t *out_counts;
 };
 
+// The greedy loop of the reference (retinanet.py:590-602) keeps the best remaining box and deletes every
+// remaining box of the same class with IoU > max_overlap.  Equivalent bitmask form, processed in rank
+// chunks of 64: (1) all threads test the chunk against the boxes kept so far and against itself
+// ((kept + 64) x 64 pairs, IoU in strict fp32), OR-ing suppression bits into shared memory; (2) one thread
+// resolves the chunk with 64-bit bit operations; (3) stop as soon as max_keep boxes are kept (later
+// survivors cannot reach the output, retinanet.py:702-704).  Work is O(K * (kept + 64)) pairs instead of
+// the K^2/2 of a full mask, and the default max_boxes = 20 usually ends after a few chunks.
 template <bool FROM_BOXES>
 __global__ void __launch_bounds__(RN_SEL_THREADS)
 rn_post_nms_kernel(const __grid_constant__ RnNmsParams P, const __grid_constant__ RnGeom g,
@@ -295,27 +374,34 @@ rn_post_nms_kernel(const __grid_constant__ RnNmsParams P, const __grid_constant_
     float *s_area = reinterpret_cast<float *>(s_box + P.top_k);
     int *s_cls = reinterpret_cast<int *>(s_area + P.top_k);
     int *s_keep = s_cls + P.top_k;
+    __shared__ unsigned long long s_sup, s_intra[64];
     __shared__ int s_nk;
 
     const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     const int K = P.nsel[b];
     const unsigned long long *sel = P.sel + (size_t)b * P.top_k;
+    const bool pack = !FROM_BOXES && P.pack;
     if (!FROM_BOXES && !P.table) rn_stage_base(g, s_base);
     __syncthreads();
 
     for (int t = tid; t < K; t += nthr) {
-        const unsigned a = 0xffffffffu - (unsigned)(sel[t] & 0xffffffffull);
+        const unsigned long long key = sel[t];
+        const int a = rn_key_anchor(key, pack);
         float4 box;
         int cls;
         if (FROM_BOXES) {
             box = P.boxes_in[a];
             cls = (int)P.classes_in[a];
         } else {
-            const float *row = P.clas + ((size_t)b * P.A + a) * P.C;
-            float best = -INFINITY;
-            cls = 0;
-            for (int c = 0; c < P.C; ++c) rn_argmax_update(__ldg(row + c), c, best, cls);
-            const float4 an = rn_anchor(g, s_base, P.table, (int)a);
+            if (pack) {
+                cls = (int)(key & 0xffull);
+            } else {
+                const float *row = P.clas + ((size_t)b * P.A + a) * P.C;
+                float best = -INFINITY;
+                cls = 0;
+                for (int c = 0; c < P.C; ++c) rn_argmax_update(__ldg(row + c), c, best, cls);
+            }
+            const float4 an = rn_anchor(g, s_base, P.table, a);
             const float4 rg = __ldg(reinterpret_cast<const float4 *>(P.reg) + (size_t)b * P.A + a);
             box = rn_decode(an, rg, dec);
         }
@@ -323,61 +409,49 @@ rn_post_nms_kernel(const __grid_constant__ RnNmsParams P, const __grid_constant_
         s_area[t] = rn_area(box);
         s_cls[t] = cls;
     }
+    if (tid == 0) s_nk = 0;
     __syncthreads();
 
-    // suppression bitmask: bit j of row i  <=>  j > i, same class, IoU(i, j) > max_overlap
-    // (retinanet.py:591-594; rows are in score-descending order)
-    const int words = (K + 63) >> 6;
-    unsigned long long *mask = P.mask + (size_t)b * P.top_k * P.words;
-    for (int item = tid; item < K * words; item += nthr) {
-        const int i = item / words, w = item - i * words;
-        unsigned long long bits = 0ull;
-        if (w * 64 + 63 > i) {
-            const float4 bi = s_box[i];
-            const float ai = s_area[i];
-            const int ci = s_cls[i];
-            const int j0 = max(w * 64, i + 1), j1 = min(w * 64 + 64, K);
-            for (int j = j0; j < j1; ++j) {
-                if (s_cls[j] == ci && rn_iou(bi, ai, s_box[j], s_area[j]) > P.max_overlap) bits |= 1ull << (j & 63);
+    int nk = 0;
+    for (int c0 = 0; c0 < K && nk < P.max_keep; c0 += 64) {
+        const int nc = min(64, K - c0);
+        if (tid < 64) s_intra[tid] = 0ull;
+        if (tid == 64) s_sup = 0ull;
+        __syncthreads();
+        const int items = (nk + nc) * 64;
+        for (int item = tid; item < items; item += nthr) {
+            const int e = item & 63, r = item >> 6;
+            if (e >= nc) continue;
+            int i;
+            if (r < nk) {
+                i = s_keep[r];
+            } else {
+                if (e <= r - nk) continue;
+                i = c0 + r - nk;
+            }
+            const int j = c0 + e;
+            // rows are score-descending: i is the better box (retinanet.py:591-594)
+            if (s_cls[i] == s_cls[j] && rn_iou(s_box[i], s_area[i], s_box[j], s_area[j]) > P.max_overlap) {
+                if (r < nk) atomicOr(&s_sup, 1ull << e);
+                else atomicOr(&s_intra[r - nk], 1ull << e);
             }
         }
-        mask[(size_t)i * words + w] = bits;
-    }
-    __syncthreads();
-
-    // sweep: one warp, lane l owns removed-words l and l+32 (top_k <= 4096), only kept rows are read
-    if (tid < 32) {
-        const int lane = tid;
-        unsigned long long rem0 = 0ull, rem1 = 0ull;
-        int nk = 0;
-        bool full = P.max_keep <= 0;
-        for (int w = 0; w < words && !full; ++w) {
-            unsigned long long cur = __shfl_sync(RN_FULL_MASK, (w < 32) ? rem0 : rem1, w & 31);
-            const int nbits = min(64, K - w * 64);
-            const unsigned long long valid = (nbits == 64) ? ~0ull : ((1ull << nbits) - 1ull);
-            unsigned long long avail = ~cur & valid;
-            while (avail) {
-                const int bit = __ffsll((long long)avail) - 1;
-                const int i = w * 64 + bit;
-                if (lane == 0) s_keep[nk] = i;
-                ++nk;
-                if (nk >= P.max_keep) {  // later survivors cannot reach the output (retinanet.py:702-704)
-                    full = true;
-                    break;
-                }
-                const unsigned long long *rowm = mask + (size_t)i * words;
-                if (lane < words) rem0 |= rowm[lane];
-                if (lane + 32 < words) rem1 |= rowm[lane + 32];
-                cur = __shfl_sync(RN_FULL_MASK, (w < 32) ? rem0 : rem1, w & 31);
-                const unsigned long long later = (bit == 63) ? 0ull : (~0ull << (bit + 1));
-                avail = ~cur & valid & later;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long alive = ~s_sup & ((nc == 64) ? ~0ull : ((1ull << nc) - 1ull));
+            int k = nk;
+            while (alive && k < P.max_keep) {
+                const int bit = __ffsll((long long)alive) - 1;
+                s_keep[k++] = c0 + bit;
+                alive &= ~s_intra[bit];
+                alive &= ~(1ull << bit);
             }
+            s_nk = k;
         }
-        if (lane == 0) s_nk = nk;
+        __syncthreads();
+        nk = s_nk;
     }
-    __syncthreads();
 
-    const int nk = s_nk;
     if (tid == 0 && P.out_counts) P.out_counts[b] = nk;
     for (int t = tid; t < nk; t += nthr) {
         const int i = s_keep[t];
@@ -386,7 +460,7 @@ rn_post_nms_kernel(const __grid_constant__ RnNmsParams P, const __grid_constant_
         if (P.out_boxes) P.out_boxes[o] = s_box[i];
         if (P.out_classes) P.out_classes[o] = (int64_t)s_cls[i];
         if (P.out_scores) P.out_scores[o] = rn_sortable_float((uint32_t)(key >> 32));
-        if (P.out_idx) P.out_idx[o] = (int32_t)(0xffffffffu - (unsigned)(key & 0xffffffffull));
+        if (P.out_idx) P.out_idx[o] = (int32_t)rn_key_anchor(key, pack);
     }
 }
 
@@ -396,17 +470,15 @@ rn_post_nms_kernel(const __grid_constant__ RnNmsParams P, const __grid_constant_
 static inline size_t rn_up256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct RnPostWs {
-    size_t counts, nsel, keys, sel, mask, total;
+    size_t counts, nsel, keys, sel, total;
 };
 static RnPostWs rn_post_layout(int B, long long cap, int top_k) {
     RnPostWs w;
-    const size_t words = (size_t)(top_k + 63) / 64;
     size_t o = 0;
     w.counts = o; o += rn_up256(sizeof(int32_t) * (size_t)B);
     w.nsel = o;   o += rn_up256(sizeof(int32_t) * (size_t)B);
     w.keys = o;   o += rn_up256(sizeof(unsigned long long) * (size_t)B * (size_t)cap);
     w.sel = o;    o += rn_up256(sizeof(unsigned long long) * (size_t)B * (size_t)top_k);
-    w.mask = o;   o += rn_up256(sizeof(unsigned long long) * (size_t)B * (size_t)top_k * words);
     w.total = o;
     return w;
 }
@@ -430,8 +502,6 @@ static int rn_launch_select_nms(bool from_boxes, int B, int cap, RnNmsParams &P,
     if (rc) return rc;
     P.sel = reinterpret_cast<unsigned long long *>(ws + L.sel);
     P.nsel = reinterpret_cast<int32_t *>(ws + L.nsel);
-    P.mask = reinterpret_cast<unsigned long long *>(ws + L.mask);
-    P.words = (P.top_k + 63) / 64;
     const size_t smem = sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4 +
                         (size_t)P.top_k * (sizeof(float4) + sizeof(float) + 2 * sizeof(int));
     cudaError_t e;
@@ -480,25 +550,28 @@ extern "C" int rn_postproc(const float *clas, const float *reg, int B, int A, in
     cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)B, s);
     if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_postproc memset: %s", cudaGetErrorString(e));
 
-    const size_t smem = sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4;
+    const size_t smem = sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4 + sizeof(unsigned long long) * RN_SCAN_ROWS;
     unsigned long long *d_keys = reinterpret_cast<unsigned long long *>(ws + L.keys);
     const float4 *table = reinterpret_cast<const float4 *>(anchors);
-    if (vec && (C / 4) % 4 == 0) {
-        const int rows = (RN_THREADS / 32) * (32 / 4) * RN_SCAN_STEPS;
-        rn_post_scan_kernel<4, 4><<<dim3((A + rows - 1) / rows, B), RN_THREADS, smem, s>>>(clas, reg, C, g, table, dec, thresh, d_keys, d_counts);
-    } else if (vec) {
-        const int rows = (RN_THREADS / 32) * 32 * RN_SCAN_STEPS;
-        rn_post_scan_kernel<4, 1><<<dim3((A + rows - 1) / rows, B), RN_THREADS, smem, s>>>(clas, reg, C, g, table, dec, thresh, d_keys, d_counts);
-    } else {
-        const int rows = (RN_THREADS / 32) * 32 * RN_SCAN_STEPS;
-        rn_post_scan_kernel<1, 1><<<dim3((A + rows - 1) / rows, B), RN_THREADS, smem, s>>>(clas, reg, C, g, table, dec, thresh, d_keys, d_counts);
-    }
+    const int pack = (A <= (1 << 24) && C <= 256) ? 1 : 0;
+#define RN_SCAN_LAUNCH(V, L, NV, R)                                                                                  \
+    do {                                                                                                             \
+        const int rows = RN_SCAN_ROWS;                                                                               \
+        rn_post_scan_kernel<V, L, NV, R><<<dim3((A + rows - 1) / rows, B), RN_THREADS, smem, s>>>(                   \
+            clas, reg, C, g, table, dec, thresh, pack, d_keys, d_counts);                                            \
+    } while (0)
+    if (vec && C == 80) RN_SCAN_LAUNCH(4, 4, 5, 2);        // COCO: 20 vectors per row = 4 lanes x 5 loads
+    else if (vec && C == 20) RN_SCAN_LAUNCH(4, 1, 5, 2);   // Pascal: 5 vectors per row, one lane per row
+    else if (vec && (C / 4) % 4 == 0) RN_SCAN_LAUNCH(4, 4, 0, 1);
+    else if (vec) RN_SCAN_LAUNCH(4, 1, 0, 1);
+    else RN_SCAN_LAUNCH(1, 1, 0, 1);
+#undef RN_SCAN_LAUNCH
     rc = rn_check_launch("rn_post_scan");
     if (rc) return rc;
 
     RnNmsParams P;
     memset(&P, 0, sizeof(P));
-    P.clas = clas; P.reg = reg; P.table = table; P.A = A; P.C = C;
+    P.clas = clas; P.reg = reg; P.table = table; P.A = A; P.C = C; P.pack = pack;
     P.top_k = top_k; P.max_keep = max_keep; P.max_overlap = max_overlap;
     P.out_boxes = reinterpret_cast<float4 *>(boxes); P.out_classes = classes; P.out_scores = scores;
     P.out_idx = anchor_idx; P.out_counts = counts;

@@ -241,3 +241,31 @@ def test_loss_full_size(H, W, C, B, M, seed):
     np.testing.assert_allclose(out3, o["out3"], rtol=RTOL, atol=0)
     rel_check(dclas, o["dclas"])
     dreg_check(dreg, o["dreg"])
+
+
+def test_captured_step_matches_eager():
+    """SSD_loss.capture(): the CUDA-graph replay gives bit-identical results to the call-by-call path,
+    also after new data is copied into the static input tensors."""
+    from neuralnetworklibrary_b200.vision import SSD_loss
+    H, W, C, B, M = 128, 160, 80, 3, 6
+    anchors = make_anchors(H, W)
+    A = anchors.shape[0]
+    data = []
+    for seed in (81, 82):
+        gb, gc = syn.make_targets(B, M, H, W, C, seed=seed, min_side=10.0, max_frac=0.7)
+        clas, reg = syn.make_train_activations(B, A, C, seed=seed)
+        data.append((clas, reg, gb, gc))
+    clas_s, reg_s = data[0][0].to(dev()), data[0][1].to(dev())
+    gb_s, gc_s = data[0][2].to(dev()), data[0][3].to(dev())
+    cap = SSD_loss().capture([anchors, reg_s, clas_s], [gb_s, gc_s])
+    for clas, reg, gb, gc in data:
+        clas_s.copy_(clas.to(dev()))
+        reg_s.copy_(reg.to(dev()))
+        gb_s.copy_(gb.to(dev()))
+        gc_s.copy_(gc.to(dev()))
+        cap.replay()
+        torch.cuda.synchronize()
+        out3, dclas, dreg, matches, npos = run_loss(anchors, clas, reg, gb, gc)
+        assert np.array_equal(cap.out3.cpu().numpy(), out3)
+        assert np.array_equal(cap.dclas.cpu().numpy(), dclas) and np.array_equal(cap.dreg.cpu().numpy(), dreg)
+        assert np.array_equal(cap.matches.cpu().numpy(), matches) and np.array_equal(cap.npos.cpu().numpy(), npos)
