@@ -14,7 +14,8 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libretina_sm100.so")
+# RETINA_B200_LIB overrides the library path (A/B comparisons of builds); the default is the in-tree build.
+LIB_PATH = os.environ.get("RETINA_B200_LIB") or os.path.join(_PKG, "libretina_sm100.so")
 SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_post.cu"]
 
 NVCC_FLAGS = [

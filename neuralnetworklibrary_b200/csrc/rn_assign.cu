@@ -25,42 +25,110 @@ rn_anchors_kernel(const __grid_constant__ RnGeom g, float4 *__restrict__ out) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Spatial culling: a CTA owns 512 consecutive anchors (a few dozen neighbouring cells of one pyramid
+// level).  Ground-truth boxes that do not touch the CTA's bounding box have IoU exactly 0 with every
+// anchor of the CTA (the intersection width or height is <= 0), so they are dropped while the image's
+// ground truth is compacted into shared memory; the survivors keep their index among the non-padding
+// rows, in ascending order, so "first maximal index" is unchanged.
 __global__ void __launch_bounds__(RN_THREADS)
 rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict__ gt_cats, int M,
                  const __grid_constant__ RnGeom g, const float4 *__restrict__ table, float pos_thr,
                  float neg_thr, int32_t *__restrict__ matches, int32_t *__restrict__ npos,
                  float *__restrict__ max_iou) {
     extern __shared__ __align__(16) unsigned char smem[];
-    // layout: base doubles | gt boxes float4[M] | gt areas float[M]
+    // layout: base doubles | gt boxes float4[M] | gt areas float[M] | gt index int[M]
     double *s_base = reinterpret_cast<double *>(smem);
     float4 *s_box = reinterpret_cast<float4 *>(smem + sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4);
     float *s_area = reinterpret_cast<float *>(s_box + M);
-    __shared__ int s_m;
+    int *s_ci = reinterpret_cast<int *>(s_area + M);
+    __shared__ float s_bb[4][RN_THREADS / 32];
+    __shared__ int s_m, s_mvalid;
     __shared__ int s_cnt[RN_THREADS / 32];
 
     const int b = blockIdx.y;
-    const int tid = threadIdx.x;
-    if (!table) rn_stage_base(g, s_base);
-    if (tid < 32) {
-        int m = rn_compact_gt(gt_boxes + (size_t)b * M, gt_cats + (size_t)b * M, M, s_box, s_area, nullptr);
-        if (tid == 0) s_m = m;
-    }
-    __syncthreads();
-    const int m = s_m;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int A = g.A;
     const int a0 = blockIdx.x * (RN_THREADS * RN_ASSIGN_APT) + tid;
+    if (!table) {
+        rn_stage_base(g, s_base);
+        __syncthreads();
+    }
 
     float4 an[RN_ASSIGN_APT];
     float aa[RN_ASSIGN_APT], best[RN_ASSIGN_APT];
     int bi[RN_ASSIGN_APT];
+    float bx1 = INFINITY, by1 = INFINITY, bx2 = -INFINITY, by2 = -INFINITY;
 #pragma unroll
     for (int i = 0; i < RN_ASSIGN_APT; ++i) {
-        int a = a0 + i * RN_THREADS;
-        an[i] = (a < A) ? rn_anchor(g, s_base, table, a) : make_float4(0.f, 0.f, 1.f, 1.f);
+        const int a = a0 + i * RN_THREADS;
+        if (a < A) {
+            an[i] = rn_anchor(g, s_base, table, a);
+            bx1 = fminf(bx1, an[i].x);
+            by1 = fminf(by1, an[i].y);
+            bx2 = fmaxf(bx2, an[i].z);
+            by2 = fmaxf(by2, an[i].w);
+        } else {
+            an[i] = make_float4(0.f, 0.f, 1.f, 1.f);
+        }
         aa[i] = rn_area(an[i]);
         best[i] = 0.0f;  // IoU >= 0 and torch.max returns index 0 for an all-zero column
         bi[i] = 0;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bx1 = fminf(bx1, __shfl_xor_sync(RN_FULL_MASK, bx1, o));
+        by1 = fminf(by1, __shfl_xor_sync(RN_FULL_MASK, by1, o));
+        bx2 = fmaxf(bx2, __shfl_xor_sync(RN_FULL_MASK, bx2, o));
+        by2 = fmaxf(by2, __shfl_xor_sync(RN_FULL_MASK, by2, o));
+    }
+    if (lane == 0) {
+        s_bb[0][warp] = bx1;
+        s_bb[1][warp] = by1;
+        s_bb[2][warp] = bx2;
+        s_bb[3][warp] = by2;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        bx1 = by1 = INFINITY;
+        bx2 = by2 = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < RN_THREADS / 32; ++w) {
+            bx1 = fminf(bx1, s_bb[0][w]);
+            by1 = fminf(by1, s_bb[1][w]);
+            bx2 = fmaxf(bx2, s_bb[2][w]);
+            by2 = fmaxf(by2, s_bb[3][w]);
+        }
+        const float4 *gb = gt_boxes + (size_t)b * M;
+        const int64_t *gc = gt_cats + (size_t)b * M;
+        int nvalid = 0, nkeep = 0;
+        for (int j0 = 0; j0 < M; j0 += 32) {
+            const int j = j0 + lane;
+            const bool valid = (j < M) && (gc[j] >= 0);  // padding rows have a negative category
+            const unsigned vmask = __ballot_sync(RN_FULL_MASK, valid);
+            float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool keep = false;
+            if (valid) {
+                bx = gb[j];
+                keep = (bx.z > bx1) && (bx.x < bx2) && (bx.w > by1) && (bx.y < by2);
+            }
+            const unsigned kmask = __ballot_sync(RN_FULL_MASK, keep);
+            if (keep) {
+                const int pos = nkeep + __popc(kmask & ((1u << lane) - 1u));
+                s_box[pos] = bx;
+                s_area[pos] = rn_area(bx);
+                s_ci[pos] = nvalid + __popc(vmask & ((1u << lane) - 1u));
+            }
+            nvalid += __popc(vmask);
+            nkeep += __popc(kmask);
+        }
+        if (lane == 0) {
+            s_m = nkeep;
+            s_mvalid = nvalid;
+        }
+    }
+    __syncthreads();
+    const int m = s_m, mvalid = s_mvalid;
+
     for (int j = 0; j < m; ++j) {
         const float4 gb = s_box[j];  // broadcast
 #pragma unroll
@@ -73,7 +141,7 @@ rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict_
                 float v = __fdiv_rn(inter, uni);
                 if (v > best[i]) {  // strict: first maximal index wins (torch.max, Vision.py:1505)
                     best[i] = v;
-                    bi[i] = j;
+                    bi[i] = s_ci[j];
                 }
             }
         }
@@ -84,7 +152,7 @@ rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict_
         int a = a0 + i * RN_THREADS;
         if (a < A) {
             int mt;
-            if (m == 0) mt = RN_MATCH_NEG;                   // Vision.py:1498-1501
+            if (mvalid == 0) mt = RN_MATCH_NEG;              // Vision.py:1498-1501
             else if (best[i] > pos_thr) mt = bi[i];          // Vision.py:1506, :1508-1509
             else if (best[i] < neg_thr) mt = RN_MATCH_NEG;   // Vision.py:1507
             else mt = RN_MATCH_IGNORE;
@@ -94,7 +162,7 @@ rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict_
         }
     }
     cnt = __reduce_add_sync(RN_FULL_MASK, cnt);
-    if ((tid & 31) == 0) s_cnt[tid >> 5] = cnt;
+    if (lane == 0) s_cnt[warp] = cnt;
     __syncthreads();
     if (tid == 0) {
         int t = 0;
@@ -165,7 +233,7 @@ extern "C" int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, i
     RnGeom g;
     int rc = rn_build_geom(&g, H, W, base, K, anchors, A);
     if (rc) return rc;
-    size_t smem = kBaseBytes + (size_t)M * (sizeof(float4) + sizeof(float));
+    size_t smem = kBaseBytes + (size_t)M * (sizeof(float4) + sizeof(float) + sizeof(int));
     if (smem > 200 * 1024) return rn_set_error(RN_ERR_INVALID_ARG, "rn_assign: M=%d too large", M);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(npos, 0, sizeof(int32_t) * (size_t)B, s);

@@ -14,8 +14,9 @@
 // contraction anywhere on this path.
 //
 // Reductions: per-thread fp32 partial sums over <= 32 elements, fixed-order warp/block trees, one
-// partial per CTA, then a single-CTA final kernel that sums the partials of each image in a fixed
-// order in float64.  No floating-point atomics anywhere => run-to-run bit-identical results.
+// partial per CTA, then a one-CTA final kernel (one warp per image) that sums each image's partials in a
+// fixed order in float64 and combines the images in image order.  No floating-point atomics anywhere
+// => run-to-run bit-identical results.
 #include "rn_common.cuh"
 
 #define RN_LOSS_U 8  // vectors per thread
@@ -32,7 +33,6 @@ struct RnLossParams {
     float *dclas;
     float *dreg;
     float *partials;  // [B][tiles][2] : {sum of focal terms, sum of smooth-L1 terms}
-    unsigned int *ticket;  // last-block election counter of the final kernel
     int B, A, C, CV, M, tiles, iters;
     float a_pos, a_neg, gamma, lo, hi;
     float wc_over_bs, wr_over_bs;  // beta / B_global, (1-beta) / B_global   (Vision.py:1644)
@@ -173,8 +173,11 @@ __device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, const flo
 // V: floats per vector (4 when C % 4 == 0, else 1).  CVT: compile-time vectors per row (0 = runtime).
 // Each CTA handles P.iters consecutive sub-tiles of one image (the prologue -- ground-truth compaction,
 // per-image scalars -- and the block reduction are paid once per CTA).
+// __launch_bounds__(256, 3): three resident CTAs per SM need <= 85 registers per thread.  Without the
+// bound ptxas drifted from 80 to 88 registers after an unrelated parameter-struct change, dropping
+// occupancy to two CTAs per SM and the kernel from 370 us to 419 us (profiles/r01_summary.md).
 template <int V, int CVT, bool G2, bool GRAD>
-__global__ void __launch_bounds__(RN_THREADS)
+__global__ void __launch_bounds__(RN_THREADS, 3)
 rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ RnGeom g) {
     extern __shared__ __align__(16) unsigned char smem[];
     // layout: gt boxes float4[M] | gt cats int[M]
@@ -273,61 +276,47 @@ rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ R
             cs += s_red[0][w];
             rs += s_red[1][w];
         }
-        float2 *out = reinterpret_cast<float2 *>(P.partials) + ((size_t)b * P.tiles + blockIdx.x);
-        *out = make_float2(cs, rs);
-        if (blockIdx.x == 0 && b == 0) *P.ticket = 0u;  // arms the final kernel's last-block election
+        reinterpret_cast<float2 *>(P.partials)[(size_t)b * gridDim.x + blockIdx.x] = make_float2(cs, rs);
     }
 }
 
-// One CTA per image: sums that image's CTA partials in a fixed order (float64), normalises like the
-// reference (Vision.py:1530, :1566).  The last CTA to finish (ticket counter, armed by the loss kernel)
-// accumulates over images in fp32 in image order (Vision.py:1640-1641) and combines (Vision.py:1643-1644).
-__global__ void __launch_bounds__(RN_THREADS)
+// One CTA, one warp per image: sums the image's CTA partials in a fixed order (float64), normalises like
+// the reference (Vision.py:1530, :1566); thread 0 then accumulates over images in fp32 in image order
+// (Vision.py:1640-1641) and combines (Vision.py:1643-1644).  (A variant that folded this into the loss
+// kernel with a last-CTA election was measured slower: every CTA then waits ~1 us for its ticket atomic
+// while holding an SM slot -- profiles/r01_summary.md.)
+__global__ void __launch_bounds__(1024)
 rn_loss_final_kernel(const float2 *__restrict__ partials, const int32_t *__restrict__ npos, int B, int tiles,
-                     float w_reg, float w_clas, float bs, float *per_image /*[B][2]*/, unsigned int *ticket,
+                     float w_reg, float w_clas, float bs, float *__restrict__ per_image /*[B][2]*/,
                      float *__restrict__ out3) {
-    __shared__ double s_c[RN_THREADS / 32], s_r[RN_THREADS / 32];
-    __shared__ bool s_last;
-    const int b = blockIdx.x, tid = threadIdx.x;
-    double cs = 0.0, rs = 0.0;
-    for (int t = tid; t < tiles; t += RN_THREADS) {
-        const float2 p = partials[(size_t)b * tiles + t];
-        cs += (double)p.x;
-        rs += (double)p.y;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        cs += __shfl_xor_sync(RN_FULL_MASK, cs, o);
-        rs += __shfl_xor_sync(RN_FULL_MASK, rs, o);
-    }
-    if ((tid & 31) == 0) {
-        s_c[tid >> 5] = cs;
-        s_r[tid >> 5] = rs;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        cs = 0.0;
-        rs = 0.0;
-#pragma unroll
-        for (int w = 0; w < RN_THREADS / 32; ++w) {
-            cs += s_c[w];
-            rs += s_r[w];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int b = warp; b < B; b += nwarps) {
+        double cs = 0.0, rs = 0.0;
+        const float2 *p = partials + (size_t)b * tiles;
+#pragma unroll 4
+        for (int t = lane; t < tiles; t += 32) {
+            const float2 v = p[t];
+            cs += (double)v.x;
+            rs += (double)v.y;
         }
-        const int n = npos[b];
-        const float n_norm = fmaxf((float)n, 1.0f);
-        per_image[2 * b + 0] = n > 0 ? __fdiv_rn((float)rs, (float)(4 * n)) : 0.0f;  // reg loss of image b
-        per_image[2 * b + 1] = __fdiv_rn((float)cs, n_norm);                          // clas loss of image b
-        __threadfence();
-        s_last = (atomicAdd(ticket, 1u) == (unsigned)(B - 1));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cs += __shfl_xor_sync(RN_FULL_MASK, cs, o);
+            rs += __shfl_xor_sync(RN_FULL_MASK, rs, o);
+        }
+        if (lane == 0) {
+            const int n = npos[b];
+            const float n_norm = fmaxf((float)n, 1.0f);
+            per_image[2 * b + 0] = n > 0 ? __fdiv_rn((float)rs, (float)(4 * n)) : 0.0f;  // reg loss of image b
+            per_image[2 * b + 1] = __fdiv_rn((float)cs, n_norm);                          // clas loss of image b
+        }
     }
     __syncthreads();
-    if (s_last && tid == 0) {
-        __threadfence();
-        const volatile float *pi = per_image;
+    if (threadIdx.x == 0) {
         float reg_total = 0.f, clas_total = 0.f;
-        for (int i = 0; i < B; ++i) {
-            reg_total = __fadd_rn(reg_total, pi[2 * i + 0]);
-            clas_total = __fadd_rn(clas_total, pi[2 * i + 1]);
+        for (int b = 0; b < B; ++b) {
+            reg_total = __fadd_rn(reg_total, per_image[2 * b + 0]);
+            clas_total = __fadd_rn(clas_total, per_image[2 * b + 1]);
         }
         const float reg_loss = __fdiv_rn(reg_total, bs), clas_loss = __fdiv_rn(clas_total, bs);
         out3[0] = __fadd_rn(__fmul_rn(w_reg, reg_loss), __fmul_rn(w_clas, clas_loss));
@@ -385,7 +374,7 @@ extern "C" size_t rn_loss_workspace_bytes(int B, int A, int C) {
     const size_t sub = (size_t)(((long long)A * (C / V) + RN_LOSS_TILE - 1) / RN_LOSS_TILE);
     size_t partials = sizeof(float2) * (size_t)B * sub;
     size_t per_image = sizeof(float) * 2 * (size_t)B;
-    return ((partials + 255) / 256) * 256 + ((per_image + 255) / 256) * 256 + 256;
+    return ((partials + 255) / 256) * 256 + ((per_image + 255) / 256) * 256;
 }
 
 template <int V, int CVT>
@@ -426,7 +415,6 @@ extern "C" int rn_loss(const float *clas, const float *reg, const float *gt_boxe
     P.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); P.gt_cats = gt_cats;
     P.matches = matches; P.npos = npos; P.table = reinterpret_cast<const float4 *>(anchors);
     P.dclas = dclas; P.dreg = dreg;
-    P.partials = reinterpret_cast<float *>(workspace);
     P.B = B; P.A = A; P.C = C; P.CV = C / V; P.M = M; P.tiles = tiles; P.iters = rn_loss_iters(B, A, C);
     P.a_pos = (float)alpha; P.a_neg = (float)(1.0 - alpha);  // Vision.py:1526
     P.gamma = (float)gamma;
@@ -437,8 +425,8 @@ extern "C" int rn_loss(const float *clas, const float *reg, const float *gt_boxe
     P.wr_over_bs = w_reg / bs;
     unsigned char *wsb = reinterpret_cast<unsigned char *>(workspace);
     const size_t ws_total = rn_loss_workspace_bytes(B, A, C);
-    float *per_image = reinterpret_cast<float *>(wsb + ws_total - 256 - ((sizeof(float) * 2 * (size_t)B + 255) / 256) * 256);
-    P.ticket = reinterpret_cast<unsigned int *>(wsb + ws_total - 256);
+    P.partials = reinterpret_cast<float *>(wsb);
+    float *per_image = reinterpret_cast<float *>(wsb + ws_total - ((sizeof(float) * 2 * (size_t)B + 255) / 256) * 256);
 
     const size_t smem = (size_t)M * (sizeof(float4) + sizeof(int));
     if (smem > 48 * 1024) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: M=%d too large", M);
@@ -451,8 +439,8 @@ extern "C" int rn_loss(const float *clas, const float *reg, const float *gt_boxe
     else rn_launch_loss<1, 0>(g2, grad, grid, smem, s, P, g);
     rc = rn_check_launch("rn_loss");
     if (rc) return rc;
-    rn_loss_final_kernel<<<B, RN_THREADS, 0, s>>>(reinterpret_cast<const float2 *>(P.partials), npos, B, tiles, w_reg,
-                                                  w_clas, bs, per_image, P.ticket, out3);
+    rn_loss_final_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const float2 *>(P.partials), npos, B, tiles, w_reg,
+                                            w_clas, bs, per_image, out3);
     return rn_check_launch("rn_loss_final");
 }
 

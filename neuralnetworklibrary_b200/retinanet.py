@@ -276,6 +276,30 @@ class BBoxPredictor(object):
                        max_boxes=20, full=False):
         """The array form of __call__: dict of host numpy arrays boxes [B,K,4] f32, classes [B,K] i64,
         scores [B,K] f32, anchor_idx [B,K] i32 (the NMS keep indices), counts [B], n_candidates [B]."""
+        dev_out = self.predict_device(height, width, reg, clas, anchors, thresh, max_overlap, top_k, max_boxes, full)
+        B = int(clas.shape[0])
+        if dev_out is None:
+            return dict(boxes=np.zeros((B, 0, 4), np.float32), classes=np.zeros((B, 0), np.int64),
+                        scores=np.zeros((B, 0), np.float32), anchor_idx=np.zeros((B, 0), np.int32),
+                        counts=np.zeros(B, np.int32), n_candidates=np.zeros(B, np.int32))
+        buf, K = dev_out
+        host = buf.cpu().numpy()   # the one device->host copy (and synchronisation) of the call
+        o_box, o_cls, o_sc, o_idx, o_cnt, o_cand, total = self._layout(B, K)
+        return dict(boxes=host[o_box:o_cls].view(np.float32).reshape(B, K, 4),
+                    classes=host[o_cls:o_sc].view(np.int64).reshape(B, K),
+                    scores=host[o_sc:o_idx].view(np.float32).reshape(B, K),
+                    anchor_idx=host[o_idx:o_cnt].view(np.int32).reshape(B, K),
+                    counts=host[o_cnt:o_cand].view(np.int32), n_candidates=host[o_cand:total].view(np.int32))
+
+    @staticmethod
+    def _layout(B, K):
+        # boxes | classes | scores | anchor_idx | counts | n_candidates  (byte offsets into one buffer)
+        return 0, 16 * B * K, 24 * B * K, 28 * B * K, 32 * B * K, 32 * B * K + 4 * B, 32 * B * K + 8 * B
+
+    def predict_device(self, height, width, reg, clas, anchors, thresh=0.05, max_overlap=0.5, top_k=1000,
+                       max_boxes=20, full=False):
+        """Launches rn_postproc on the current stream and returns (uint8 device buffer, K) without any
+        host synchronisation (None when nothing can be returned); predict_arrays() decodes the buffer."""
         _lib.require_cuda(clas, "clas", torch.float32)
         _lib.require_cuda(reg, "reg", torch.float32)
         clas, reg = clas.detach().contiguous(), reg.detach().contiguous()
@@ -284,21 +308,16 @@ class BBoxPredictor(object):
             raise ValueError("expected reg [B,A,4], clas [B,A,C], anchors [A,4]")
         top_k = int(top_k)
         dev = clas.device
-        empty = dict(boxes=np.zeros((B, 0, 4), np.float32), classes=np.zeros((B, 0), np.int64),
-                     scores=np.zeros((B, 0), np.float32), anchor_idx=np.zeros((B, 0), np.int32),
-                     counts=np.zeros(B, np.int32), n_candidates=np.zeros(B, np.int32))
         if top_k < 1 or (not full and int(max_boxes) < 1) or B == 0:
-            return empty
+            return None
         if top_k > _lib.MAX_TOP_K:
             raise ValueError("top_k > %d is not supported" % _lib.MAX_TOP_K)
         K = top_k if full else min(int(max_boxes), top_k)
         lib = _lib.load()
         H, W, base, Kc, table, _ = anchor_args(anchors, height, width)
-        # one device buffer for every output => one device->host copy
-        o_box, o_cls, o_sc, o_idx, o_cnt, o_cand = 0, 16 * B * K, 24 * B * K, 28 * B * K, 32 * B * K, 32 * B * K + 4 * B
-        total = 32 * B * K + 8 * B
+        o_box, o_cls, o_sc, o_idx, o_cnt, o_cand, total = self._layout(B, K)
         with torch.cuda.device(dev):
-            buf = torch.empty(total, dtype=torch.uint8, device=dev)
+            buf = torch.empty(total, dtype=torch.uint8, device=dev)   # one buffer => one device->host copy
             ws = _ws.get(lib.rn_postproc_workspace_bytes(B, A, top_k), dev)
             p = buf.data_ptr()
             _lib.check(lib.rn_postproc(
@@ -307,9 +326,4 @@ class BBoxPredictor(object):
                 float(thresh), float(max_overlap), top_k, K,
                 C.c_void_p(p + o_box), C.c_void_p(p + o_cls), C.c_void_p(p + o_sc), C.c_void_p(p + o_idx),
                 C.c_void_p(p + o_cnt), C.c_void_p(p + o_cand), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
-            host = buf.cpu().numpy()
-        return dict(boxes=host[o_box:o_cls].view(np.float32).reshape(B, K, 4),
-                    classes=host[o_cls:o_sc].view(np.int64).reshape(B, K),
-                    scores=host[o_sc:o_idx].view(np.float32).reshape(B, K),
-                    anchor_idx=host[o_idx:o_cnt].view(np.int32).reshape(B, K),
-                    counts=host[o_cnt:o_cand].view(np.int32), n_candidates=host[o_cand:total].view(np.int32))
+        return buf, K

@@ -130,7 +130,7 @@ class _SSDLossFunction(torch.autograd.Function):
 
 class CapturedLossStep(object):
     """SSD_loss forward+backward for fixed shapes, captured once into a CUDA graph and replayed with a
-    single launch (assignment, fused loss + gradients, final reduction).  For launch-bound loops: the
+    single launch (assignment kernel + fused loss/gradient/reduction kernel).  For launch-bound loops: the
     whole step is ~0.1-0.5 ms of GPU time, less than the Python / launch overhead of issuing its pieces.
 
     The tensors passed to SSD_loss.capture() are the static inputs: copy new data into them (`.copy_`)
