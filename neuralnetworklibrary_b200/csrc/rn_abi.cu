@@ -53,16 +53,29 @@ int rn_build_geom(RnGeom *g, int H, int W, const double *base, int K, const floa
     if (expect <= 0 || expect != A)
         return rn_set_error(RN_ERR_INVALID_ARG, "A=%d does not match the %d anchors of a %dx%d image with K=%d", A,
                             expect, H, W, K);
-    int off = 0;
+    int off = 0, offc = 0;
     for (int l = 0; l < RN_NUM_LEVELS; ++l) {
         int s = 8 << l;
         g->gh[l] = (H + s - 1) / s;
         g->gw[l] = (W + s - 1) / s;
         g->off[l] = off;
+        g->offc[l] = offc;
         off += g->gh[l] * g->gw[l] * K;
-        for (int k = 0; k < K; ++k)
-            for (int j = 0; j < 4; ++j) g->base[(l * RN_MAX_K + k) * 4 + j] = base[(l * K + k) * 4 + j];
+        offc += g->gh[l] * g->gw[l];
+        double hw = 0.0, hh = 0.0;
+        for (int k = 0; k < K; ++k) {
+            for (int j = 0; j < 4; ++j) {
+                double v = base[(l * K + k) * 4 + j];
+                g->base[(l * RN_MAX_K + k) * 4 + j] = v;
+                double a = v < 0 ? -v : v;
+                if ((j & 1) == 0) hw = a > hw ? a : hw;
+                else hh = a > hh ? a : hh;
+            }
+        }
+        g->hw[l] = hw;
+        g->hh[l] = hh;
     }
     g->off[RN_NUM_LEVELS] = off;
+    g->offc[RN_NUM_LEVELS] = offc;
     return RN_OK;
 }

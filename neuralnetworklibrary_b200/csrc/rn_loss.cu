@@ -93,6 +93,76 @@ __device__ __forceinline__ float rn_focal_elem(float x, float lo, float hi, floa
     return (p == x) ? g : 0.0f;  // clamp backward: pass-through iff lo <= x <= hi (inclusive)
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): one instruction issues two fp32
+// operations.  The loss kernel is limited by instruction issue, not by the fp32 pipes, so packing the
+// arithmetic of two neighbouring class elements halves the issue slots the polynomial and the
+// focal-term algebra need (profiles/r01_summary.md).  Each half is an ordinary IEEE fp32 operation.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long rn_f2;
+__device__ __forceinline__ rn_f2 rn_pack(float a, float b) {
+    rn_f2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void rn_unpack(rn_f2 v, float &a, float &b) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ rn_f2 rn_fma2(rn_f2 a, rn_f2 b, rn_f2 c) {
+    rn_f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ rn_f2 rn_mul2(rn_f2 a, rn_f2 b) {
+    rn_f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ rn_f2 rn_add2(rn_f2 a, rn_f2 b) {
+    rn_f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ rn_f2 rn_splat(float a) { return rn_pack(a, a); }
+
+// Two background (target 0) class elements with gamma == 2: same mathematics as
+// rn_focal_elem<false, true, GRAD>, arithmetic packed two-wide.  acc2 accumulates pw * (-2 log q).
+template <bool GRAD>
+__device__ __forceinline__ void rn_focal_pair_neg(float x0, float x1, float lo, float hi, float ga, rn_f2 &acc2,
+                                                  float &g0, float &g1) {
+    const float p0 = fminf(fmaxf(x0, lo), hi), p1 = fminf(fmaxf(x1, lo), hi);  // Vision.py:1524
+    const rn_f2 one = rn_splat(1.0f), mone = rn_splat(-1.0f);
+    const rn_f2 q = rn_fma2(rn_pack(p0, p1), mone, one);  // 1 - p  (exact product, one rounding)
+    const rn_f2 u = rn_fma2(q, mone, one);                // 1 - (1 - p), Vision.py:1525-1527
+    float q0, q1;
+    rn_unpack(q, q0, q1);
+    // -2 log(q): range reduction per element (integer), polynomial packed
+    const int i0 = __float_as_int(q0), i1 = __float_as_int(q1);
+    const int t0 = (i0 - 0x3f3504f3) & 0xff800000, t1 = (i1 - 0x3f3504f3) & 0xff800000;
+    const rn_f2 f = rn_add2(rn_pack(__int_as_float(i0 - t0), __int_as_float(i1 - t1)), mone);
+    const rn_f2 e23 = rn_pack((float)t0, (float)t1);
+    rn_f2 p = rn_splat(-2.0f * 8.700362962e-02f);
+    p = rn_fma2(p, f, rn_splat(-2.0f * -1.426749380e-01f));
+    p = rn_fma2(p, f, rn_splat(-2.0f * 1.491478973e-01f));
+    p = rn_fma2(p, f, rn_splat(-2.0f * -1.657758280e-01f));
+    p = rn_fma2(p, f, rn_splat(-2.0f * 1.996306205e-01f));
+    p = rn_fma2(p, f, rn_splat(-2.0f * -2.500133718e-01f));
+    p = rn_fma2(p, f, rn_splat(-2.0f * 3.333391077e-01f));
+    const rn_f2 z = rn_mul2(f, f);
+    const rn_f2 w0 = rn_fma2(rn_splat(-2.0f), f, z);
+    const rn_f2 r = rn_fma2(rn_mul2(z, f), p, w0);
+    const rn_f2 l2 = rn_fma2(e23, rn_splat(-2.0f * 0.69314718056f / 8388608.0f), r);
+    const rn_f2 pw = rn_mul2(u, u);  // pow(x, 2.0) == x*x in torch
+    acc2 = rn_fma2(pw, l2, acc2);
+    if (!GRAD) return;
+    // dl/dp / (alpha weight) = pw / q - 2 u log q = pw * rcp(q) + u * l2
+    rn_f2 g = rn_fma2(u, l2, rn_mul2(pw, rn_pack(rn_rcp_approx(q0), rn_rcp_approx(q1))));
+    g = rn_mul2(g, rn_splat(ga));
+    rn_unpack(g, g0, g1);
+    g0 = (p0 == x0) ? g0 : 0.0f;  // clamp backward: pass-through iff lo <= x <= hi (inclusive)
+    g1 = (p1 == x1) ? g1 : 0.0f;
+}
+
 template <int V>
 struct RnVec;
 template <>
@@ -151,8 +221,17 @@ __device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, const flo
             slow = (unsigned)pe < (unsigned)V;
         }
         if (!slow) {  // common case: every element has target 0
+            if (V == 4 && G2) {
+                rn_f2 acc2 = 0ull;  // (+0.0f, +0.0f)
+                rn_focal_pair_neg<GRAD>(xv[u].at(0), xv[u].at(1), P.lo, P.hi, ga, acc2, gv.at(0), gv.at(1));
+                rn_focal_pair_neg<GRAD>(xv[u].at(2), xv[u].at(3), P.lo, P.hi, ga, acc2, gv.at(2), gv.at(3));
+                float s0, s1;
+                rn_unpack(acc2, s0, s1);
+                part = s0 + s1;
+            } else {
 #pragma unroll
-            for (int e = 0; e < V; ++e) gv.at(e) = rn_focal_elem<false, G2, GRAD>(xv[u].at(e), P.lo, P.hi, P.gamma, ga, part);
+                for (int e = 0; e < V; ++e) gv.at(e) = rn_focal_elem<false, G2, GRAD>(xv[u].at(e), P.lo, P.hi, P.gamma, ga, part);
+            }
         } else {
 #pragma unroll
             for (int e = 0; e < V; ++e) {
