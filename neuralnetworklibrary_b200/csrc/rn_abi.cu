@@ -1,6 +1,7 @@
 // rn_abi.cu -- error state, geometry and the small host-only entry points of libretina_sm100.so.
 #include <stdarg.h>
 #include <stdio.h>
+#include <math.h>
 #include <string.h>
 
 #include "rn_common.cuh"
@@ -74,6 +75,8 @@ int rn_build_geom(RnGeom *g, int H, int W, const double *base, int K, const floa
         }
         g->hw[l] = hw;
         g->hh[l] = hh;
+        g->hwf[l] = nextafterf((float)hw, INFINITY);  // >= hw whatever way the cast rounded
+        g->hhf[l] = nextafterf((float)hh, INFINITY);
     }
     g->off[RN_NUM_LEVELS] = off;
     g->offc[RN_NUM_LEVELS] = offc;

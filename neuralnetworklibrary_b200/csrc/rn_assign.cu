@@ -25,7 +25,7 @@ rn_anchors_kernel(const __grid_constant__ RnGeom g, float4 *__restrict__ out) {
 
 // ------------------------------------------------------------------------------------------------
 // Assignment kernel.  SPLIT threads per grid CELL, each holding KT / SPLIT of the cell's K base boxes
-// in registers; a CTA walks `tiles_per_cta` consecutive tiles of RN_ASSIGN_CELLS cells of ONE image.
+// in registers; persistent CTAs, each working on ONE image, whose warps walk warp-tiles round-robin.
 //   * prologue, once per CTA: the float64 base table is staged in shared memory and one warp compacts
 //     the image's non-padding ground truth (rows with a negative category are padding,
 //     Vision.py:1637-1638) into shared memory.  Earlier versions did this once per 128 cells; the kernel
@@ -40,21 +40,22 @@ rn_anchors_kernel(const __grid_constant__ RnGeom g, float4 *__restrict__ out) {
 //     index" (Vision.py:1505); the IEEE divide only runs for overlapping pairs;
 //   * each thread stores its anchors' results directly: a warp writes one contiguous 4*32*KPT-byte run.
 // In table mode (caller-supplied anchors) every anchor is its own "cell" (K = 1, KT = 0).
-#define RN_ASSIGN_CELLS 128
+#define RN_ASSIGN_CELLS 64
 
 template <int KT, int SPLIT>
-__global__ void __launch_bounds__(RN_ASSIGN_CELLS * SPLIT, SPLIT == 3 ? 3 : 4)
+__global__ void __launch_bounds__(RN_ASSIGN_CELLS * SPLIT, 5)
 rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict__ gt_cats, int M,
                  const __grid_constant__ RnGeom g, const float4 *__restrict__ table, float pos_thr,
-                 float neg_thr, int tiles_per_cta, int32_t *__restrict__ matches, int32_t *__restrict__ npos,
+                 float neg_thr, int32_t *__restrict__ matches, int32_t *__restrict__ npos,
                  float *__restrict__ max_iou) {
     extern __shared__ __align__(16) unsigned char smem[];
-    // layout: base doubles | gt boxes float4[M] | gt areas float[M]
+    // layout: gt boxes float4[M] | gt areas float[M].  The float64 base table is read straight from the
+    // kernel parameters (constant bank): staging it in shared memory with per-lane indices serialises on
+    // the constant cache and cost every CTA several microseconds (profiles/r01_summary.md).
     constexpr int NTHR = RN_ASSIGN_CELLS * SPLIT;
     constexpr int KPT = KT > 0 ? KT / SPLIT : 1;  // anchors per thread on the register path
     const int K = table ? 1 : (KT ? KT : g.K);
-    double *s_base = reinterpret_cast<double *>(smem);
-    float4 *s_box = reinterpret_cast<float4 *>(smem + sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4);
+    float4 *s_box = reinterpret_cast<float4 *>(smem);
     float *s_area = reinterpret_cast<float *>(s_box + M);
     __shared__ int s_mvalid;
     __shared__ int s_cnt[NTHR / 32];
@@ -63,16 +64,10 @@ rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncell = table ? g.A : g.offc[RN_NUM_LEVELS];
     const int A = g.A;
-    const int lc = tid / SPLIT, part = tid - lc * SPLIT;  // local cell, anchor group inside the cell
 
     if (warp == 0) {
         const int mv = rn_compact_gt(gt_boxes + (size_t)b * M, gt_cats + (size_t)b * M, M, s_box, s_area, nullptr);
         if (lane == 0) s_mvalid = mv;
-    } else if (!table) {
-        for (int i = tid - 32; i < RN_NUM_LEVELS * g.K * 4; i += NTHR - 32) {
-            const int lv = i / (g.K * 4), r = i - lv * (g.K * 4);
-            s_base[i] = g.base[lv * RN_MAX_K * 4 + r];
-        }
     }
     __syncthreads();
     const int m = s_mvalid;
@@ -98,10 +93,19 @@ rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict_
         }
     };
 
-    const int tile0 = blockIdx.x * tiles_per_cta;
+    // Work unit = one warp-tile of 32 consecutive (cell, anchor-group) slots.  Warp-tiles are dealt
+    // round-robin over all warps that work on this image: the tiles of the coarse pyramid levels, whose huge
+    // anchors overlap every ground-truth box and cost ~20x a P3 tile, end up on different warps.  With
+    // contiguous per-CTA ranges one CTA per image owned all of them and the whole kernel waited for it (SMs
+    // 45 % idle, profiles/r01_summary.md).  Nothing inside the loop needs a CTA barrier.
+    const int nslots = table ? ncell : ncell * SPLIT;
+    const int nwt = (nslots + 31) >> 5;
+    const int gwarps = gridDim.x * (NTHR / 32);
 #pragma unroll 1
-    for (int t = 0; t < tiles_per_cta; ++t) {
-        const int c = (tile0 + t) * RN_ASSIGN_CELLS + lc;
+    for (int wt = blockIdx.x * (NTHR / 32) + warp; wt < nwt; wt += gwarps) {
+        const int slot = (wt << 5) + lane;
+        const int c = table ? slot : slot / SPLIT;
+        const int part = table ? 0 : slot - c * SPLIT;  // anchor group inside the cell
         const bool live = c < ncell;
         if (KT > 0 && !table) {
             // decode the cell; conservative bounding box of all its anchors (rounded outwards).  Lanes past
@@ -112,27 +116,27 @@ rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict_
             const int local = cc - g.offc[l];
             const int gw = g.gw[l];
             const int iy = local / gw, ix = local - iy * gw;
-            const double stride = (double)(8 << l);
-            const double sx = __dmul_rn((double)ix + 0.5, stride);  // retinanet.py:458 (exact)
-            const double sy = __dmul_rn((double)iy + 0.5, stride);  // retinanet.py:459
-            const float bx1 = live ? __double2float_rd(sx - g.hw[l]) : INFINITY;
-            const float bx2 = live ? __double2float_ru(sx + g.hw[l]) : -INFINITY;
-            const float by1 = live ? __double2float_rd(sy - g.hh[l]) : INFINITY;
-            const float by2 = live ? __double2float_ru(sy + g.hh[l]) : -INFINITY;
+            // The cell's conservative bounding box in fp32 only: the cell centre (i + 0.5) * stride is
+            // exact in fp32, the level's largest half extent is rounded up, and the subtraction / addition
+            // round outwards -- so the box contains every anchor of the cell, and no float64 is touched
+            // unless a ground-truth box actually reaches the cell.
+            const float strf = (float)(8 << l);
+            const float sxf = ((float)ix + 0.5f) * strf, syf = ((float)iy + 0.5f) * strf;
+            const float bx1 = live ? __fsub_rd(sxf, g.hwf[l]) : INFINITY;
+            const float bx2 = live ? __fadd_ru(sxf, g.hwf[l]) : -INFINITY;
+            const float by1 = live ? __fsub_rd(syf, g.hhf[l]) : INFINITY;
+            const float by2 = live ? __fadd_ru(syf, g.hhf[l]) : -INFINITY;
             float4 an[KPT];
             float aa[KPT], best[KPT];
             int bi[KPT];
 #pragma unroll
             for (int i = 0; i < KPT; ++i) {
-                const double *bb = s_base + (l * KT + part * KPT + i) * 4;
-                an[i].x = __double2float_rn(__dadd_rn(bb[0], sx));
-                an[i].y = __double2float_rn(__dadd_rn(bb[1], sy));
-                an[i].z = __double2float_rn(__dadd_rn(bb[2], sx));
-                an[i].w = __double2float_rn(__dadd_rn(bb[3], sy));
-                aa[i] = rn_area(an[i]);
+                an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                aa[i] = 0.0f;
                 best[i] = 0.0f;  // IoU >= 0 and torch.max returns index 0 for an all-zero column
                 bi[i] = 0;
             }
+            bool have_anchors = false;  // generated lazily, on the first box that reaches the cell
             // Warp-level cull: lane j tests ground-truth box j against the bounding box of the warp's
             // ~11 neighbouring cells; only boxes that touch it are visited (ascending index), and each
             // thread still skips a box that misses its own cell.  Typically 1-3 of M boxes survive.
@@ -156,6 +160,21 @@ rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict_
                     cand &= cand - 1;
                     const float4 gb = s_box[j];  // broadcast
                     if (gb.z > bx1 && gb.x < bx2 && gb.w > by1 && gb.y < by2) {
+                        if (!have_anchors) {
+                            have_anchors = true;
+                            const double stride = (double)(8 << l);
+                            const double sx = __dmul_rn((double)ix + 0.5, stride);  // retinanet.py:458 (exact)
+                            const double sy = __dmul_rn((double)iy + 0.5, stride);  // retinanet.py:459
+#pragma unroll
+                            for (int i = 0; i < KPT; ++i) {
+                                const double *bb = g.base + (l * RN_MAX_K + part * KPT + i) * 4;
+                                an[i].x = __double2float_rn(__dadd_rn(bb[0], sx));
+                                an[i].y = __double2float_rn(__dadd_rn(bb[1], sy));
+                                an[i].z = __double2float_rn(__dadd_rn(bb[2], sx));
+                                an[i].w = __double2float_rn(__dadd_rn(bb[3], sy));
+                                aa[i] = rn_area(an[i]);
+                            }
+                        }
                         const float ga = s_area[j];
 #pragma unroll
                         for (int i = 0; i < KPT; ++i) pair(an[i], aa[i], gb, ga, j, best[i], bi[i]);
@@ -187,7 +206,7 @@ rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict_
                 if (table) {
                     an = __ldg(table + c);
                 } else {
-                    const double *bb = s_base + (l * K + k) * 4;
+                    const double *bb = g.base + (l * RN_MAX_K + k) * 4;
                     an.x = __double2float_rn(__dadd_rn(bb[0], sx));
                     an.y = __double2float_rn(__dadd_rn(bb[1], sy));
                     an.z = __double2float_rn(__dadd_rn(bb[2], sx));
@@ -278,7 +297,7 @@ extern "C" int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, i
     int rc = rn_build_geom(&g, H, W, base, K, anchors, A);
     if (rc) return rc;
     const int ncell = anchors ? A : g.offc[RN_NUM_LEVELS];
-    size_t smem = kBaseBytes + (size_t)M * (sizeof(float4) + sizeof(float));
+    size_t smem = (size_t)M * (sizeof(float4) + sizeof(float));
     if (smem > 200 * 1024) return rn_set_error(RN_ERR_INVALID_ARG, "rn_assign: M=%d too large", M);
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(npos, 0, sizeof(int32_t) * (size_t)B, s);
@@ -289,14 +308,17 @@ extern "C" int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, i
                : cudaFuncSetAttribute(rn_assign_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_assign smem: %s", cudaGetErrorString(e));
     }
-    // One wave: about three CTAs per SM in total (the resident limit), each walking several tiles of one image.
-    const int tiles = (ncell + RN_ASSIGN_CELLS - 1) / RN_ASSIGN_CELLS;
-    int per_cta = (int)(((long long)tiles * B + 3 * 148 - 1) / (3 * 148));
-    if (per_cta < 1) per_cta = 1;
-    dim3 grid((tiles + per_cta - 1) / per_cta, B);
+    // One wave of persistent CTAs: five per SM in total (the resident limit), split evenly over images.
+    const int nthr = k9 ? RN_ASSIGN_CELLS * 3 : RN_ASSIGN_CELLS;
+    const long long nwt = ((long long)ncell * (k9 ? 3 : 1) + 31) / 32;
+    int ctas = (5 * 148 + B - 1) / B;
+    const long long max_ctas = (nwt + nthr / 32 - 1) / (nthr / 32);
+    if (ctas > max_ctas) ctas = (int)max_ctas;
+    if (ctas < 1) ctas = 1;
+    dim3 grid(ctas, B);
     const float4 *gb4 = reinterpret_cast<const float4 *>(gt_boxes), *tb4 = reinterpret_cast<const float4 *>(anchors);
-    if (k9) rn_assign_kernel<9, 3><<<grid, RN_ASSIGN_CELLS * 3, smem, s>>>(gb4, gt_cats, M, g, tb4, pos_thr, neg_thr, per_cta, matches, npos, max_iou);
-    else rn_assign_kernel<0, 1><<<grid, RN_ASSIGN_CELLS, smem, s>>>(gb4, gt_cats, M, g, tb4, pos_thr, neg_thr, per_cta, matches, npos, max_iou);
+    if (k9) rn_assign_kernel<9, 3><<<grid, nthr, smem, s>>>(gb4, gt_cats, M, g, tb4, pos_thr, neg_thr, matches, npos, max_iou);
+    else rn_assign_kernel<0, 1><<<grid, nthr, smem, s>>>(gb4, gt_cats, M, g, tb4, pos_thr, neg_thr, matches, npos, max_iou);
     return rn_check_launch("rn_assign");
 }
 

@@ -25,6 +25,7 @@ struct RnGeom {
     int off[RN_NUM_LEVELS + 1];               // first anchor index of each level; off[5] = A
     int offc[RN_NUM_LEVELS + 1];              // first cell index of each level; offc[5] = number of cells
     double hw[RN_NUM_LEVELS], hh[RN_NUM_LEVELS];  // largest |x| / |y| extent of the level's base boxes
+    float hwf[RN_NUM_LEVELS], hhf[RN_NUM_LEVELS]; // the same, rounded UP to float32
     double base[RN_NUM_LEVELS * RN_MAX_K * 4];  // size_l * anchor_set, float64 (retinanet.py:492)
 };
 
