@@ -107,6 +107,17 @@ def device_activations(B, A, C, seed, device, mu):
     return clas, reg
 
 
+def measured_traffic(kernel, B_per_launch, ref_B):
+    """DRAM bytes per launch from the committed ncu capture (profiles/r01_traffic.json), scaled to the batch of
+    this run if it differs from the captured one (traffic is linear in the image count); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)[kernel]["traffic_bytes"]
+        return int(round(t * B_per_launch / ref_B))
+    except Exception:
+        return None
+
+
 def loss_bytes(B, A, C, grad=True):
     return (8 if grad else 4) * A * (C + 4) * B
 
@@ -370,7 +381,8 @@ def run_ours(args):
                     "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": None, "kernel": "rn_loss_kernel<4,20,true,true>",
+                         "frac": round(achieved / peak, 4), "traffic": measured_traffic("rn_loss_kernel<4,20,true,true>", B, 16),
+                         "traffic_source": "ncu --set full capture, profiles/r01_traffic.json", "kernel": "rn_loss_kernel<4,20,true,true>",
                          "kernel_ms": round(kern_ms, 4), "algorithmic_bytes": alg, "peak_source": peak_src,
                          "timed": "CUDA events around every rn_loss call of the eager pass (same inputs, same process)",
                          "whole_step_frac": round(alg * args.steps / (total_ms * 1e-3) / 1e9 / peak, 4)},

@@ -167,16 +167,19 @@ class CapturedLossStep(object):
 
 def reduce_loss_scalars(out3, group=None):
     """The one collective of the path: sums the three per-rank loss scalars over the image shards.
-    all_gather + a fixed rank-order sum (not all_reduce) so the result is bit-identical on every rank
-    and independent of the reduction algorithm NCCL picks."""
+    all_gather + one fixed-order sum over the rank axis (not all_reduce), so the result is bit-identical on
+    every rank and independent of the reduction algorithm NCCL picks.  12 bytes per rank: pure latency."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    parts = [torch.empty_like(out3) for _ in range(world)]
-    dist.all_gather(parts, out3.contiguous(), group=group)
-    total = parts[0].clone()
-    for p in parts[1:]:
-        total += p
-    return total
+    out3 = out3.contiguous()
+    if out3.is_cuda:
+        gathered = torch.empty((world, out3.numel()), dtype=out3.dtype, device=out3.device)
+        dist.all_gather_into_tensor(gathered, out3, group=group)   # NCCL
+    else:                                                           # gloo (CPU tests of the host logic)
+        parts = [torch.empty_like(out3) for _ in range(world)]
+        dist.all_gather(parts, out3, group=group)
+        gathered = torch.stack(parts)
+    return gathered.sum(dim=0)
 
 
 class SSD_loss(object):
