@@ -361,9 +361,9 @@ rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ R
 
 // One CTA, one warp per image: sums the image's CTA partials in a fixed order (float64), normalises like
 // the reference (Vision.py:1530, :1566); thread 0 then accumulates over images in fp32 in image order
-// (Vision.py:1640-1641) and combines (Vision.py:1643-1644).  (A variant that folded this into the loss
-// kernel with a last-CTA election was measured slower: every CTA then waits ~1 us for its ticket atomic
-// while holding an SM slot -- profiles/r01_summary.md.)
+// (Vision.py:1640-1641) and combines (Vision.py:1643-1644).  (Folding this into the loss kernel
+// with a last-CTA election -- __threadfence + ticket atomic per CTA -- was measured slower twice, also when
+// only warp 0 stays for the election: COCO step 0.378 -> 0.393 ms, Pascal 78 -> 87 us; profiles/r01_summary.md.)
 __global__ void __launch_bounds__(1024)
 rn_loss_final_kernel(const float2 *__restrict__ partials, const int32_t *__restrict__ npos, int B, int tiles,
                      float w_reg, float w_clas, float bs, float *__restrict__ per_image /*[B][2]*/,
