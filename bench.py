@@ -96,13 +96,15 @@ class ClockSampler(object):
 # --------------------------------------------------------------------------------------------------
 # synthetic inputs
 # --------------------------------------------------------------------------------------------------
-def device_activations(B, A, C, seed, device, mu):
-    """clas = sigmoid(N(mu,1)) and reg ~ N(0,0.25) generated on the device."""
+def device_activations(B, A, C, seed, device, mu, logits=False):
+    """clas = sigmoid(N(mu,1)) (or the logits themselves) and reg ~ N(0,0.25) generated on the device
+    (SURVEY.md section 8d)."""
     import torch
     g = torch.Generator(device=device).manual_seed(seed)
     clas = torch.empty((B, A, C), dtype=torch.float32, device=device)
     for i in range(B):  # per image to bound the temporaries
-        clas[i] = torch.sigmoid(torch.randn((A, C), generator=g, device=device) + mu)
+        z = torch.randn((A, C), generator=g, device=device) + mu
+        clas[i] = z if logits else torch.sigmoid(z)
     reg = torch.randn((B, A, 4), generator=g, device=device) * 0.5
     return clas, reg
 
@@ -125,7 +127,7 @@ def loss_bytes(B, A, C, grad=True):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
-def make_loss_sets(cfg, B, device, nbuf, seed):
+def make_loss_sets(cfg, B, device, nbuf, seed, logits=False):
     import torch
 
     from neuralnetworklibrary_b200 import testing as syn
@@ -136,13 +138,13 @@ def make_loss_sets(cfg, B, device, nbuf, seed):
     A = anchors.shape[0]
     sets = []
     for k in range(nbuf):
-        clas, reg = device_activations(B, A, C, seed + 17 * k, device, mu=-4.6)
+        clas, reg = device_activations(B, A, C, seed + 17 * k, device, mu=-4.6, logits=logits)
         gb, gc = syn.make_targets(B, M, H, W, C, seed=seed + 17 * k)
         sets.append((clas, reg, gb.to(device), gc.to(device)))
     return anchors, sets
 
 
-def time_loss_graph(anchors, sets, steps, warmup, device, world):
+def time_loss_graph(anchors, sets, steps, warmup, device, world, from_logits=False):
     """`steps` replays of the captured step (assign kernel + fused loss fwd/bwd/reduction kernel),
     rotating over the input sets; with several ranks each step ends with the 12-byte loss exchange."""
     import torch
@@ -150,7 +152,7 @@ def time_loss_graph(anchors, sets, steps, warmup, device, world):
 
     from neuralnetworklibrary_b200.vision import SSD_loss, reduce_loss_scalars
 
-    loss_fn = SSD_loss(global_batch=sets[0][0].shape[0] * world)
+    loss_fn = SSD_loss(global_batch=sets[0][0].shape[0] * world, from_logits=from_logits)
     caps = [loss_fn.capture([anchors, reg, clas], [gb, gc]) for clas, reg, gb, gc in sets]
 
     def step(k):
@@ -414,6 +416,17 @@ def run_ours(args):
                               "roofline_frac_whole_step": round(loss_bytes(32, pA, 20) * psteps / (pt * 1e-3) / 1e9 / peak, 4)}
         except Exception as exc:
             line["pascal"] = {"error": repr(exc)}
+        try:  # the head's sigmoid fused into the loss kernel (logits in)
+            lan, lsets = make_loss_sets(COCO, B, device, 2, 1005, logits=True)
+            lt, _, _ = time_loss_graph(lan, lsets, args.steps, args.warmup, device, 1, from_logits=True)
+            del lsets
+            line["logits"] = {"workload": "coco_loss_fwd_bwd from logits (head sigmoid fused), B=%d 800x1344 C=80" % B,
+                              "images_per_s": round(B * args.steps / (lt * 1e-3), 1), "ms_per_step": round(lt / args.steps, 4),
+                              "roofline_frac_whole_step": round(loss_bytes(B, A, COCO["C"]) * args.steps / (lt * 1e-3) / 1e9 / peak, 4),
+                              "note": "also removes one read+write pass over [B,A,C] from the model's forward and one from its "
+                                      "backward (not counted here)"}
+        except Exception as exc:
+            line["logits"] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_baseline_loss(COCO)
             line["cpu_baseline"] = {"value": round(v, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}

@@ -93,6 +93,18 @@ int rn_loss(const float *clas, const float *reg, const float *gt_boxes, const in
             double gamma, double beta, int B_global, float *dclas, float *dreg, float *out3,
             void *workspace, size_t workspace_bytes, void *stream);
 
+/* Same as rn_loss, but the class activations are LOGITS: the head's nn.Sigmoid (retinanet.py:258, :286) is
+ * fused into the kernel (y = 1/(1+exp(-z)), accurate expf + IEEE divide as torch's CUDA sigmoid) and
+ * dlogits = d loss / d logits (chained through sigmoid's backward, grad*(1-y)*y).  SURVEY.md section 8f row 1:
+ * not a drop-in (ObjectDetectionNet.forward must return logits); it removes one full read+write pass over
+ * [B,A,C] from the model's forward and one from its backward.  probs_out ([B,A,C], may be NULL) receives
+ * sigmoid(logits) exactly as the kernel used it (for inference-time reuse and for parity checks). */
+int rn_loss_logits(const float *logits, const float *reg, const float *gt_boxes, const int64_t *gt_cats,
+                   const int32_t *matches, const int32_t *npos, int B, int A, int C, int M, int H, int W,
+                   const double *base /*host*/, int K, const float *anchors /*or NULL*/, double alpha,
+                   double gamma, double beta, int B_global, float *dlogits, float *dreg, float *probs_out,
+                   float *out3, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Backward with a non-unit upstream gradient: scales dclas[n_clas], dreg[n_reg] in place by the
  * DEVICE scalar *grad_out; the kernel exits immediately when *grad_out == 1 (what loss.backward()
  * passes, General/Learner.py:514), so the common case costs one empty launch and no host sync. */

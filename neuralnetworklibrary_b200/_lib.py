@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "-fmad=false",  # never contract a*b+c behind our back; fused ops are spelled fmaf() explicitly
+    "-split-compile", "0",  # build-time only: ptxas works on the kernels of a translation unit in parallel
     "-Xcompiler", "-fPIC", "-shared",
 ]
 
@@ -77,6 +78,9 @@ PROTOTYPES = {
     "rn_loss": (C.c_int, [_f32p, _f32p, _f32p, _i64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                           C.c_int, _f64p, C.c_int, _f32p, C.c_double, C.c_double, C.c_double, C.c_int,
                           _f32p, _f32p, _f32p, _vp, C.c_size_t, _vp]),
+    "rn_loss_logits": (C.c_int, [_f32p, _f32p, _f32p, _i64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, _f64p, C.c_int, _f32p, C.c_double, C.c_double, C.c_double, C.c_int,
+                                 _f32p, _f32p, _f32p, _f32p, _vp, C.c_size_t, _vp]),
     "rn_scale_grads": (C.c_int, [_f32p, C.c_size_t, _f32p, C.c_size_t, _f32p, _vp]),
     "rn_postproc_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rn_postproc": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _f32p,

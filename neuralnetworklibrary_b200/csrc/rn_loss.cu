@@ -32,6 +32,7 @@ struct RnLossParams {
     const float4 *table;
     float *dclas;
     float *dreg;
+    float *probs;     // LOGITS only, may be NULL: sigmoid(logits) as used by the kernel (for checking / reuse)
     float *partials;  // [B][tiles][2] : {sum of focal terms, sum of smooth-L1 terms}
     int B, A, C, CV, M, tiles, iters;
     float a_pos, a_neg, gamma, lo, hi;
@@ -63,6 +64,12 @@ __device__ __forceinline__ float rn_rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+
+// LOGITS variant: the class activations are logits and the head's
+// nn.Sigmoid (reference retinanet.py:258,286) is fused here.  y = 1 / (1 + exp(-z)) with the accurate expf
+// and an IEEE divide -- the operations torch's CUDA sigmoid kernel performs -- and the gradient is chained
+// through sigmoid's backward, grad * (1 - y) * y.
+__device__ __forceinline__ float rn_sigmoid(float z) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-z))); }
 
 // One class element.  POS selects the target (t = 1 for the matched class of a positive anchor).
 // Returns the gradient w.r.t. the probability (already scaled by `ga` = alpha-weight * upstream) and
@@ -183,7 +190,7 @@ struct RnVec<1> {
 // One sub-tile of RN_LOSS_TILE vectors: U independent 128-bit loads per thread are issued first, then
 // the element math, then the stores.  FULL = the sub-tile lies completely inside the image, so there is
 // no per-vector bounds predicate; addresses are one 64-bit base per thread plus immediates.
-template <int V, int CVT, bool G2, bool GRAD, bool FULL>
+template <int V, int CVT, bool G2, bool GRAD, bool FULL, bool LOGITS>
 __device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, const float *__restrict__ x_img,
                                                 float *__restrict__ dx_img, const int32_t *__restrict__ m_img,
                                                 const int *s_cat, int CV, int nvec, int tile0, float gl,
@@ -213,6 +220,9 @@ __device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, const flo
         const float ga = a_row * gl;
         float part = 0.0f;
         RnVec<V> gv;
+        float y[V];  // probabilities: the input itself, or sigmoid(logit)
+#pragma unroll
+        for (int e = 0; e < V; ++e) y[e] = LOGITS ? rn_sigmoid(xv[u].at(e)) : xv[u].at(e);
         bool slow = false;
         int pe = -1;
         if (m >= 0) {  // rare: a positive anchor; is its class inside this vector?  (Vision.py:1588-1593)
@@ -223,26 +233,35 @@ __device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, const flo
         if (!slow) {  // common case: every element has target 0
             if (V == 4 && G2) {
                 rn_f2 acc2 = 0ull;  // (+0.0f, +0.0f)
-                rn_focal_pair_neg<GRAD>(xv[u].at(0), xv[u].at(1), P.lo, P.hi, ga, acc2, gv.at(0), gv.at(1));
-                rn_focal_pair_neg<GRAD>(xv[u].at(2), xv[u].at(3), P.lo, P.hi, ga, acc2, gv.at(2), gv.at(3));
+                rn_focal_pair_neg<GRAD>(y[0], y[1], P.lo, P.hi, ga, acc2, gv.at(0), gv.at(1));
+                rn_focal_pair_neg<GRAD>(y[2], y[3], P.lo, P.hi, ga, acc2, gv.at(2), gv.at(3));
                 float s0, s1;
                 rn_unpack(acc2, s0, s1);
                 part = s0 + s1;
             } else {
 #pragma unroll
-                for (int e = 0; e < V; ++e) gv.at(e) = rn_focal_elem<false, G2, GRAD>(xv[u].at(e), P.lo, P.hi, P.gamma, ga, part);
+                for (int e = 0; e < V; ++e) gv.at(e) = rn_focal_elem<false, G2, GRAD>(y[e], P.lo, P.hi, P.gamma, ga, part);
             }
         } else {
 #pragma unroll
             for (int e = 0; e < V; ++e) {
                 if (e == pe) {
                     float pp = 0.0f;
-                    gv.at(e) = rn_focal_elem<true, G2, GRAD>(xv[u].at(e), P.lo, P.hi, P.gamma, P.a_pos * gl, pp);
+                    gv.at(e) = rn_focal_elem<true, G2, GRAD>(y[e], P.lo, P.hi, P.gamma, P.a_pos * gl, pp);
                     acc_pos = fmaf(0.5f * P.a_pos, pp, acc_pos);
                 } else {
-                    gv.at(e) = rn_focal_elem<false, G2, GRAD>(xv[u].at(e), P.lo, P.hi, P.gamma, ga, part);
+                    gv.at(e) = rn_focal_elem<false, G2, GRAD>(y[e], P.lo, P.hi, P.gamma, ga, part);
                 }
             }
+        }
+        if (LOGITS && P.probs != nullptr && (FULL || v0 + u * RN_THREADS < nvec)) {
+            float *pp = P.probs + ((size_t)blockIdx.y * nvec + v0 + (size_t)u * RN_THREADS) * V;
+#pragma unroll
+            for (int e = 0; e < V; ++e) pp[e] = y[e];
+        }
+        if (LOGITS && GRAD) {  // sigmoid backward: grad * (1 - y) * y
+#pragma unroll
+            for (int e = 0; e < V; ++e) gv.at(e) = (gv.at(e) * (1.0f - y[e])) * y[e];
         }
         acc_neg = fmaf(0.5f * a_row, part, acc_neg);
         if (GRAD && (FULL || v0 + u * RN_THREADS < nvec)) gv.store(dp + (size_t)u * RN_THREADS * V);
@@ -255,7 +274,7 @@ __device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, const flo
 // __launch_bounds__(256, 3): three resident CTAs per SM need <= 85 registers per thread.  Without the
 // bound ptxas drifted from 80 to 88 registers after an unrelated parameter-struct change, dropping
 // occupancy to two CTAs per SM and the kernel from 370 us to 419 us (profiles/r01_summary.md).
-template <int V, int CVT, bool G2, bool GRAD>
+template <int V, int CVT, bool G2, bool GRAD, bool LOGITS>
 __global__ void __launch_bounds__(RN_THREADS, 3)
 rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ RnGeom g) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -286,9 +305,9 @@ rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ R
 #pragma unroll 1
     for (int tile0 = cta0; tile0 < cta1; tile0 += RN_LOSS_TILE) {
         if (tile0 + RN_LOSS_TILE <= nvec)
-            rn_loss_subtile<V, CVT, G2, GRAD, true>(P, x_img, dx_img, m_img, s_cat, CV, nvec, tile0, gl, acc_neg, acc_pos);
+            rn_loss_subtile<V, CVT, G2, GRAD, true, LOGITS>(P, x_img, dx_img, m_img, s_cat, CV, nvec, tile0, gl, acc_neg, acc_pos);
         else
-            rn_loss_subtile<V, CVT, G2, GRAD, false>(P, x_img, dx_img, m_img, s_cat, CV, nvec, tile0, gl, acc_neg, acc_pos);
+            rn_loss_subtile<V, CVT, G2, GRAD, false, LOGITS>(P, x_img, dx_img, m_img, s_cat, CV, nvec, tile0, gl, acc_neg, acc_pos);
     }
 
     // ---- regression rows whose first vector lies in this CTA's range: smooth L1 (Vision.py:1532-1566) ----
@@ -456,20 +475,44 @@ extern "C" size_t rn_loss_workspace_bytes(int B, int A, int C) {
     return ((partials + 255) / 256) * 256 + ((per_image + 255) / 256) * 256;
 }
 
-template <int V, int CVT>
+template <int V, int CVT, bool LOGITS>
 static void rn_launch_loss(bool g2, bool grad, dim3 grid, size_t smem, cudaStream_t s, const RnLossParams &P,
                            const RnGeom &g) {
-    if (g2 && grad) rn_loss_kernel<V, CVT, true, true><<<grid, RN_THREADS, smem, s>>>(P, g);
-    else if (g2) rn_loss_kernel<V, CVT, true, false><<<grid, RN_THREADS, smem, s>>>(P, g);
-    else if (grad) rn_loss_kernel<V, CVT, false, true><<<grid, RN_THREADS, smem, s>>>(P, g);
-    else rn_loss_kernel<V, CVT, false, false><<<grid, RN_THREADS, smem, s>>>(P, g);
+    if (g2 && grad) rn_loss_kernel<V, CVT, true, true, LOGITS><<<grid, RN_THREADS, smem, s>>>(P, g);
+    else if (g2) rn_loss_kernel<V, CVT, true, false, LOGITS><<<grid, RN_THREADS, smem, s>>>(P, g);
+    else if (grad) rn_loss_kernel<V, CVT, false, true, LOGITS><<<grid, RN_THREADS, smem, s>>>(P, g);
+    else rn_loss_kernel<V, CVT, false, false, LOGITS><<<grid, RN_THREADS, smem, s>>>(P, g);
 }
+
+static int rn_loss_impl(bool logits, float *probs, const float *clas, const float *reg, const float *gt_boxes,
+                        const int64_t *gt_cats, const int32_t *matches, const int32_t *npos, int B, int A, int C, int M,
+                        int H, int W, const double *base, int K, const float *anchors, double alpha, double gamma,
+                        double beta, int B_global, float *dclas, float *dreg, float *out3, void *workspace,
+                        size_t workspace_bytes, void *stream);
 
 extern "C" int rn_loss(const float *clas, const float *reg, const float *gt_boxes, const int64_t *gt_cats,
                        const int32_t *matches, const int32_t *npos, int B, int A, int C, int M, int H, int W,
                        const double *base, int K, const float *anchors, double alpha, double gamma, double beta,
                        int B_global, float *dclas, float *dreg, float *out3, void *workspace,
                        size_t workspace_bytes, void *stream) {
+    return rn_loss_impl(false, nullptr, clas, reg, gt_boxes, gt_cats, matches, npos, B, A, C, M, H, W, base, K, anchors, alpha,
+                        gamma, beta, B_global, dclas, dreg, out3, workspace, workspace_bytes, stream);
+}
+
+extern "C" int rn_loss_logits(const float *logits, const float *reg, const float *gt_boxes, const int64_t *gt_cats,
+                              const int32_t *matches, const int32_t *npos, int B, int A, int C, int M, int H, int W,
+                              const double *base, int K, const float *anchors, double alpha, double gamma,
+                              double beta, int B_global, float *dlogits, float *dreg, float *probs_out, float *out3,
+                              void *workspace, size_t workspace_bytes, void *stream) {
+    return rn_loss_impl(true, probs_out, logits, reg, gt_boxes, gt_cats, matches, npos, B, A, C, M, H, W, base, K, anchors, alpha,
+                        gamma, beta, B_global, dlogits, dreg, out3, workspace, workspace_bytes, stream);
+}
+
+static int rn_loss_impl(bool logits, float *probs, const float *clas, const float *reg, const float *gt_boxes,
+                        const int64_t *gt_cats, const int32_t *matches, const int32_t *npos, int B, int A, int C, int M,
+                        int H, int W, const double *base, int K, const float *anchors, double alpha, double gamma,
+                        double beta, int B_global, float *dclas, float *dreg, float *out3, void *workspace,
+                        size_t workspace_bytes, void *stream) {
     if (B <= 0 || A <= 0 || C <= 0 || M < 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: B=%d A=%d C=%d M=%d", B, A, C, M);
     if (!clas || !reg || !matches || !npos || !out3 || (M > 0 && (!gt_boxes || !gt_cats)))
         return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: null pointer");
@@ -493,7 +536,7 @@ extern "C" int rn_loss(const float *clas, const float *reg, const float *gt_boxe
     P.clas = clas; P.reg = reg;
     P.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); P.gt_cats = gt_cats;
     P.matches = matches; P.npos = npos; P.table = reinterpret_cast<const float4 *>(anchors);
-    P.dclas = dclas; P.dreg = dreg;
+    P.dclas = dclas; P.dreg = dreg; P.probs = probs;
     P.B = B; P.A = A; P.C = C; P.CV = C / V; P.M = M; P.tiles = tiles; P.iters = rn_loss_iters(B, A, C);
     P.a_pos = (float)alpha; P.a_neg = (float)(1.0 - alpha);  // Vision.py:1526
     P.gamma = (float)gamma;
@@ -512,10 +555,17 @@ extern "C" int rn_loss(const float *clas, const float *reg, const float *gt_boxe
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(tiles, B);
     const bool g2 = (gamma == 2.0), grad = dclas != nullptr;
-    if (V == 4 && C == 80) rn_launch_loss<4, 20>(g2, grad, grid, smem, s, P, g);
-    else if (V == 4 && C == 20) rn_launch_loss<4, 5>(g2, grad, grid, smem, s, P, g);
-    else if (V == 4) rn_launch_loss<4, 0>(g2, grad, grid, smem, s, P, g);
-    else rn_launch_loss<1, 0>(g2, grad, grid, smem, s, P, g);
+    if (logits) {
+        if (V == 4 && C == 80) rn_launch_loss<4, 20, true>(g2, grad, grid, smem, s, P, g);
+        else if (V == 4 && C == 20) rn_launch_loss<4, 5, true>(g2, grad, grid, smem, s, P, g);
+        else if (V == 4) rn_launch_loss<4, 0, true>(g2, grad, grid, smem, s, P, g);
+        else rn_launch_loss<1, 0, true>(g2, grad, grid, smem, s, P, g);
+    } else {
+        if (V == 4 && C == 80) rn_launch_loss<4, 20, false>(g2, grad, grid, smem, s, P, g);
+        else if (V == 4 && C == 20) rn_launch_loss<4, 5, false>(g2, grad, grid, smem, s, P, g);
+        else if (V == 4) rn_launch_loss<4, 0, false>(g2, grad, grid, smem, s, P, g);
+        else rn_launch_loss<1, 0, false>(g2, grad, grid, smem, s, P, g);
+    }
     rc = rn_check_launch("rn_loss");
     if (rc) return rc;
     rn_loss_final_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const float2 *>(P.partials), npos, B, tiles, w_reg,

@@ -81,10 +81,16 @@ def _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, need_grad, bufs=Non
     _lib.check(lib.rn_assign(_lib.ptr(gt_boxes), _lib.ptr(gt_cats), B, M, H, W, base, K, table, A,
                              float(cfg["pos_thresh"]), float(cfg["neg_thresh"]), _lib.ptr(matches), _lib.ptr(npos),
                              None, stream))
-    _lib.check(lib.rn_loss(_lib.ptr(clas), _lib.ptr(reg), _lib.ptr(gt_boxes), _lib.ptr(gt_cats),
-                           _lib.ptr(matches), _lib.ptr(npos), B, A, Cn, M, H, W, base, K, table,
-                           float(cfg["alpha"]), float(cfg["gamma"]), float(cfg["beta"]), int(B_global),
-                           _lib.ptr(dclas), _lib.ptr(dreg), _lib.ptr(out3), _lib.ptr(ws), ws.numel(), stream))
+    common = (_lib.ptr(clas), _lib.ptr(reg), _lib.ptr(gt_boxes), _lib.ptr(gt_cats), _lib.ptr(matches), _lib.ptr(npos),
+              B, A, Cn, M, H, W, base, K, table, float(cfg["alpha"]), float(cfg["gamma"]), float(cfg["beta"]),
+              int(B_global), _lib.ptr(dclas), _lib.ptr(dreg))
+    tail = (_lib.ptr(out3), _lib.ptr(ws), ws.numel(), stream)
+    if cfg.get("from_logits"):
+        probs = torch.empty_like(clas) if cfg.get("want_probs") else None
+        cfg["last_probs"] = probs
+        _lib.check(lib.rn_loss_logits(*(common + (_lib.ptr(probs),) + tail)))
+    else:
+        _lib.check(lib.rn_loss(*(common + tail)))
     return out3, dreg, dclas, matches, npos
 
 
@@ -190,8 +196,13 @@ class SSD_loss(object):
     world size): the kernels scale by 1/global_batch and the three scalars are summed over ranks with one
     12-byte NCCL exchange; per-rank reg/clas gradients need no communication."""
 
-    def __init__(self, beta=0.5, alpha=0.25, gamma=2.0, distributed=False, process_group=None, global_batch=None):
+    def __init__(self, beta=0.5, alpha=0.25, gamma=2.0, distributed=False, process_group=None, global_batch=None,
+                 from_logits=False, keep_probs=False):
         self.beta, self.alpha, self.gamma = beta, alpha, gamma
+        self.keep_probs = bool(keep_probs)   # from_logits only: also store sigmoid(logits) in .last_probs
+        # from_logits=True: `clas` holds logits and the head's nn.Sigmoid (reference retinanet.py:258,286) is
+        # fused into the loss kernel (SURVEY.md section 8f row 1; needs a head that returns logits)
+        self.from_logits = bool(from_logits)
         self.distributed, self.process_group, self.global_batch = distributed, process_group, global_batch
         self.pos_thresh, self.neg_thresh = 0.5, 0.4   # defaults of match_anchors_objects, Vision.py:1474
         self.reg_loss = self.clas_loss = None
@@ -211,7 +222,7 @@ class SSD_loss(object):
             world = dist.get_world_size(self.process_group)
         cfg = dict(alpha=self.alpha, gamma=self.gamma, beta=self.beta, pos_thresh=self.pos_thresh,
                    neg_thresh=self.neg_thresh, world_size=world, group=self.process_group,
-                   global_batch=self.global_batch)
+                   global_batch=self.global_batch, from_logits=self.from_logits, want_probs=self.keep_probs)
         loss, reg_loss, clas_loss = _SSDLossFunction.apply(reg.contiguous(), clas.contiguous(), anchors, gt_boxes,
                                                            gt_cats, cfg)
         self._cfg = cfg
@@ -231,8 +242,14 @@ class SSD_loss(object):
             if not t.is_contiguous():
                 raise ValueError("capture() needs contiguous static tensors")
         cfg = dict(alpha=self.alpha, gamma=self.gamma, beta=self.beta, pos_thresh=self.pos_thresh,
-                   neg_thresh=self.neg_thresh, world_size=1, group=None, global_batch=self.global_batch)
+                   neg_thresh=self.neg_thresh, world_size=1, group=None, global_batch=self.global_batch,
+                   from_logits=self.from_logits)
         return CapturedLossStep(cfg, anchors, reg.detach(), clas.detach(), BBoxes, Cats)
+
+    @property
+    def last_probs(self):
+        """sigmoid(logits) exactly as the kernel used it (from_logits=True, keep_probs=True), else None."""
+        return self._cfg.get("last_probs")
 
     @property
     def last_assignment(self):

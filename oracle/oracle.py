@@ -57,6 +57,10 @@ def lib():
         L.orc_loss.argtypes = [_f32p, _f32p, _f32p, _f32p, _i64p, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_double, C.c_double, C.c_double, C.c_int, C.c_float, C.c_float,
                                _f32p, _f32p, _f32p, _i32p, _i32p]
+        L.orc_loss_logits.restype = None
+        L.orc_loss_logits.argtypes = L.orc_loss.argtypes
+        L.orc_sigmoid.restype = None
+        L.orc_sigmoid.argtypes = [_f32p, C.c_size_t, _f32p]
         L.orc_nms.restype = C.c_int
         L.orc_nms.argtypes = [_f32p, _i64p, _f32p, C.c_int, C.c_float, C.c_int, C.c_int, _i32p]
         L.orc_postproc_batch.restype = None
@@ -117,8 +121,9 @@ def assign(anchors_, gt_boxes, gt_cats, pos_thr=0.5, neg_thr=0.4):
 
 
 def loss(anchors_, clas, reg, gt_boxes, gt_cats, alpha=0.25, gamma=2.0, beta=0.5, B_global=None,
-         pos_thr=0.5, neg_thr=0.4, want_grads=True, want_matches=False):
-    """Batch loss. Returns dict(out3, dclas, dreg, matches, npos)."""
+         pos_thr=0.5, neg_thr=0.4, want_grads=True, want_matches=False, from_logits=False):
+    """Batch loss. Returns dict(out3, dclas, dreg, matches, npos).  from_logits: `clas` holds logits, the
+    sigmoid of the classification head is applied first and dclas is the gradient w.r.t. the logits."""
     an, cl, rg = _f32(anchors_), _f32(clas), _f32(reg)
     B, A, Cc = cl.shape
     gb = _f32(gt_boxes).reshape(B, -1, 4)
@@ -129,11 +134,20 @@ def loss(anchors_, clas, reg, gt_boxes, gt_cats, alpha=0.25, gamma=2.0, beta=0.5
     dreg = np.empty_like(rg) if want_grads else None
     matches = np.empty((B, A), dtype=np.int32) if want_matches else None
     npos = np.empty(B, dtype=np.int32)
-    lib().orc_loss(_ptr(an, _f32p), _ptr(cl, _f32p), _ptr(rg, _f32p), _ptr(gb, _f32p), _ptr(gc, _i64p),
-                   B, A, Cc, M, float(alpha), float(gamma), float(beta), int(B_global or B),
-                   np.float32(pos_thr), np.float32(neg_thr), _ptr(out3, _f32p), _ptr(dclas, _f32p),
-                   _ptr(dreg, _f32p), _ptr(matches, _i32p), _ptr(npos, _i32p))
+    fn = lib().orc_loss_logits if from_logits else lib().orc_loss
+    fn(_ptr(an, _f32p), _ptr(cl, _f32p), _ptr(rg, _f32p), _ptr(gb, _f32p), _ptr(gc, _i64p),
+       B, A, Cc, M, float(alpha), float(gamma), float(beta), int(B_global or B),
+       np.float32(pos_thr), np.float32(neg_thr), _ptr(out3, _f32p), _ptr(dclas, _f32p),
+       _ptr(dreg, _f32p), _ptr(matches, _i32p), _ptr(npos, _i32p))
     return dict(out3=out3, dclas=dclas, dreg=dreg, matches=matches, npos=npos)
+
+
+def sigmoid(z):
+    """fp32 sigmoid exactly as orc_loss_logits applies it."""
+    z = _f32(z)
+    y = np.empty_like(z)
+    lib().orc_sigmoid(_ptr(z, _f32p), z.size, _ptr(y, _f32p))
+    return y
 
 
 def nms(boxes, classes, scores, max_overlap=0.5, top_k=1000, max_boxes=20):

@@ -400,6 +400,27 @@ void orc_loss(const float *anchors, const float *clas, const float *reg, const f
     free(clas_per_img);
 }
 
+/* torch.sigmoid in fp32: 1 / (1 + exp(-z)) (the head's output activation, retinanet.py:258, :286). */
+void orc_sigmoid(const float *z, size_t n, float *y) {
+    for (size_t i = 0; i < n; ++i) y[i] = 1.0f / (1.0f + expf(-z[i]));
+}
+
+/* SSD_loss on LOGITS: the head's nn.Sigmoid (retinanet.py:258, :286) followed by SSD_loss, and the gradient
+ * chained through sigmoid's backward (grad * (1 - y) * y).  SURVEY.md section 8f row 1. */
+void orc_loss_logits(const float *anchors, const float *logits, const float *reg, const float *gt_boxes,
+                     const int64_t *gt_cats, int B, int A, int C, int M, double alpha, double gamma, double beta,
+                     int B_global, float pos_thr, float neg_thr, float *out3, float *dlogits, float *dreg,
+                     int32_t *matches_out, int32_t *npos_out) {
+    size_t n = (size_t)B * A * C;
+    float *y = (float *)malloc(sizeof(float) * (n > 0 ? n : 1));
+    orc_sigmoid(logits, n, y);
+    orc_loss(anchors, y, reg, gt_boxes, gt_cats, B, A, C, M, alpha, gamma, beta, B_global, pos_thr, neg_thr, out3,
+             dlogits, dreg, matches_out, npos_out);
+    if (dlogits)
+        for (size_t i = 0; i < n; ++i) dlogits[i] = (dlogits[i] * (1.0f - y[i])) * y[i]; /* sigmoid_backward */
+    free(y);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Post-processing: Applications/VisionModels/retinanet.py:523-812
  * ---------------------------------------------------------------------------------------------- */

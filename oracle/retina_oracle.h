@@ -14,6 +14,7 @@
 #ifndef RETINA_ORACLE_H
 #define RETINA_ORACLE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -53,6 +54,16 @@ void orc_loss(const float *anchors, const float *clas, const float *reg, const f
               const int64_t *gt_cats, int B, int A, int C, int M, double alpha, double gamma,
               double beta, int B_global, float pos_thr, float neg_thr, float *out3, float *dclas,
               float *dreg, int32_t *matches_out, int32_t *npos_out);
+
+/* torch.sigmoid in fp32 (the classification head's output activation, retinanet.py:258, :286). */
+void orc_sigmoid(const float *z, size_t n, float *y);
+
+/* The same on LOGITS: nn.Sigmoid of the classification head (retinanet.py:258, :286) + SSD_loss, gradient
+ * w.r.t. the logits. */
+void orc_loss_logits(const float *anchors, const float *logits, const float *reg, const float *gt_boxes,
+                     const int64_t *gt_cats, int B, int A, int C, int M, double alpha, double gamma, double beta,
+                     int B_global, float pos_thr, float neg_thr, float *out3, float *dlogits, float *dreg,
+                     int32_t *matches_out, int32_t *npos_out);
 
 /* nms with rel_thresh/inc/dup = None: retinanet.py:523-711 (sort :573-576, greedy :590-602, cap
  * :702-704).  Ties in score are ordered by ascending input index (the reference's torch.sort is

@@ -23,14 +23,15 @@ def assign(anchors_, boxes, cats):
     return pos.numpy(), neg.numpy(), matches.numpy()
 
 
-def loss(anchors_, clas, reg, gt_boxes, gt_cats, beta=0.5, alpha=0.25, gamma=2.0):
-    """SSD_loss forward + autograd backward. Returns dict(out3, dclas, dreg)."""
+def loss(anchors_, clas, reg, gt_boxes, gt_cats, beta=0.5, alpha=0.25, gamma=2.0, from_logits=False):
+    """SSD_loss forward + autograd backward. Returns dict(out3, dclas, dreg).  from_logits: `clas` holds
+    logits and the classification head's nn.Sigmoid (retinanet.py:258,286) is applied before the loss."""
     _, vis = ref_shim.load()
     an = torch.as_tensor(anchors_)
     cl = torch.as_tensor(clas).clone().requires_grad_(True)
     rg = torch.as_tensor(reg).clone().requires_grad_(True)
     f = vis.SSD_loss(beta=beta, alpha=alpha, gamma=gamma)
-    out = f([an, rg, cl], [torch.as_tensor(gt_boxes), torch.as_tensor(gt_cats)])
+    out = f([an, rg, torch.nn.Sigmoid()(cl) if from_logits else cl], [torch.as_tensor(gt_boxes), torch.as_tensor(gt_cats)])
     out.backward()
     out3 = np.array([out.item(), float(f.reg_loss), float(f.clas_loss)], dtype=np.float32)
     dreg = rg.grad.numpy() if rg.grad is not None else np.zeros_like(np.asarray(reg))

@@ -269,3 +269,40 @@ def test_captured_step_matches_eager():
         assert np.array_equal(cap.out3.cpu().numpy(), out3)
         assert np.array_equal(cap.dclas.cpu().numpy(), dclas) and np.array_equal(cap.dreg.cpu().numpy(), dreg)
         assert np.array_equal(cap.matches.cpu().numpy(), matches) and np.array_equal(cap.npos.cpu().numpy(), npos)
+
+
+@pytest.mark.parametrize("seed,H,W,C,B,M,kw", [(91, 128, 160, 80, 2, 6, {}), (92, 100, 167, 20, 3, 5, dict(beta=0.3, alpha=0.4)),
+                                               (93, 96, 96, 7, 2, 4, {}), (94, 64, 96, 12, 2, 4, dict(gamma=1.5))])
+def test_loss_from_logits(seed, H, W, C, B, M, kw):
+    """the head's sigmoid fused into the loss kernel (rn_loss_logits).
+
+    The reference's focal term contains 1-(1-p), quantised to ulp(1): one ulp of p = sigmoid(z) (CUDA expf vs
+    the host libm) moves it by up to 6e-4 relative at p = 1e-4.  The check therefore feeds the oracle the
+    kernel's own probabilities (probs_out) and chains sigmoid's backward, grad*(1-y)*y, in fp32; the fused
+    sigmoid itself must be within 4 ulp of the correctly rounded value and equal to torch's CUDA sigmoid."""
+    from neuralnetworklibrary_b200.vision import SSD_loss
+    anchors, an = make_anchors(H, W), orc.anchors(H, W)
+    gb, gc = syn.make_targets(B, M, H, W, C, seed=seed, min_side=10.0, max_frac=0.7)
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(B, an.shape[0], C, generator=g) * 1.5 - 4.6
+    logits.view(-1)[:64] = torch.linspace(-12, 12, 64)       # both clamp ends and the ill-conditioned large-p side
+    reg = torch.randn(B, an.shape[0], 4, generator=g) * 0.5
+    f = SSD_loss(from_logits=True, keep_probs=True, **kw)
+    zd, rd = logits.to(dev()).requires_grad_(True), reg.to(dev()).requires_grad_(True)
+    loss = f([anchors, rd, zd], [gb.to(dev()), gc.to(dev())])
+    loss.backward()
+    y = f.last_probs.cpu().numpy()
+    exact = 1.0 / (1.0 + np.exp(-logits.numpy().astype(np.float64)))
+    ulp = np.abs(y.view(np.int32).astype(np.int64) - exact.astype(np.float32).view(np.int32).astype(np.int64))
+    assert ulp.max() <= 4      # expf (2 ulp) + add + divide
+    assert np.array_equal(y, torch.sigmoid(logits.to(dev())).cpu().numpy())   # torch's CUDA sigmoid, bit for bit
+    o = orc.loss(an, y, reg.numpy(), gb.numpy(), gc.numpy(), want_matches=True, **kw)
+    got3 = np.array([loss.item(), f.reg_loss.item(), f.clas_loss.item()], np.float32)
+    np.testing.assert_allclose(got3, o["out3"], rtol=RTOL, atol=0)
+    rel_check(zd.grad.cpu().numpy(), (o["dclas"] * (np.float32(1) - y)) * y)
+    dreg_check(rd.grad.cpu().numpy(), o["dreg"])
+    # and the probability path on the same probabilities gives the identical loss value
+    f2 = SSD_loss(**kw)
+    with torch.no_grad():
+        l2 = f2([anchors, reg.to(dev()), f.last_probs], [gb.to(dev()), gc.to(dev())])
+    assert l2.item() == loss.item()

@@ -47,3 +47,33 @@ def test_postproc(seed, mu):
             assert np.array_equal(np.array(rc[i]), o["classes"][i, :n])
             assert np.array_equal(np.array(rs[i]), o["scores"][i, :n])
             np.testing.assert_allclose(o["boxes"][i, :n], np.stack(rb[i]), rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("seed,H,W,C,B,M", [(14, 128, 128, 20, 2, 5), (15, 96, 160, 80, 2, 8)])
+def test_loss_from_logits(seed, H, W, C, B, M):
+    """head sigmoid + SSD_loss, gradient w.r.t. the logits.
+
+    The reference's focal term uses 1-(1-p) (Vision.py:1525-1527), which is quantised to ulp(1) = 6e-8: a
+    1-ulp difference in p = sigmoid(z) between two libms moves it by up to 6e-4 relative at p = 1e-4.  So the
+    chain is checked with the reference's own sigmoid values, and the oracle's sigmoid separately."""
+    import torch
+    an = orc.anchors(H, W)
+    gb, gc = syn.make_targets(B, M, H, W, C, seed=seed, min_side=12.0, max_frac=0.6)
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(B, an.shape[0], C, generator=g) - 4.6     # the head's prior-0.01 init, Vision.py:1434
+    reg = torch.randn(B, an.shape[0], 4, generator=g) * 0.5
+    r = ref.loss(an, logits, reg, gb, gc, from_logits=True)
+    y = torch.sigmoid(logits).numpy()
+    o = orc.loss(an, y, reg.numpy(), gb.numpy(), gc.numpy())
+    np.testing.assert_allclose(o["out3"], r["out3"], rtol=1e-5, atol=0)
+    assert_rel((o["dclas"] * (np.float32(1) - y)) * y, r["dclas"])          # sigmoid backward: grad*(1-y)*y
+    assert_rel(o["dreg"], r["dreg"])
+    # the oracle's own logits entry point: same loss; same gradient wherever its sigmoid equals torch's bitwise
+    o2 = orc.loss(an, logits.numpy(), reg.numpy(), gb.numpy(), gc.numpy(), from_logits=True)
+    np.testing.assert_allclose(o2["out3"], r["out3"], rtol=1e-5, atol=0)
+    y2 = orc.sigmoid(logits.numpy())
+    same = y2 == y
+    assert same.mean() > 0.5
+    assert_rel(np.where(same, o2["dclas"], 0), np.where(same, r["dclas"], 0))
+    ulp = np.abs(y2.view(np.int32).astype(np.int64) - y.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 2
