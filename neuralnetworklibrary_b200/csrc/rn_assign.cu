@@ -65,6 +65,7 @@ rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict_
     const int ncell = table ? g.A : g.offc[RN_NUM_LEVELS];
     const int A = g.A;
 
+    rn_pdl_trigger();  // the loss kernel that follows may start filling SMs as this grid's CTAs retire
     if (warp == 0) {
         const int mv = rn_compact_gt(gt_boxes + (size_t)b * M, gt_cats + (size_t)b * M, M, s_box, s_area, nullptr);
         if (lane == 0) s_mvalid = mv;

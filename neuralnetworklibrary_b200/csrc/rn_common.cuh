@@ -60,6 +60,32 @@ __device__ __forceinline__ void rn_stg_stream(float4 *p, float4 v) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still draining; rn_pdl_wait() blocks until
+// the predecessor has completed and its writes are visible (a no-op for an ordinary launch), and
+// rn_pdl_trigger() lets the successor's CTAs be scheduled as this grid's CTAs retire.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rn_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void rn_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Launch helper: same as <<<grid, block, smem, stream>>> plus the PDL attribute.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t rn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                        Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Warp / block reductions (fixed order => deterministic)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float rn_warp_sum(float v) {

@@ -292,6 +292,12 @@ rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ R
     const int cta1 = min(nvec, cta0 + RN_LOSS_TILE * P.iters);
 
     if (tid < 32) rn_compact_gt(P.gt_boxes + (size_t)b * P.M, P.gt_cats + (size_t)b * P.M, P.M, s_box, nullptr, s_cat);
+    {   // Launched with PDL right behind rn_assign: pull this CTA's first sub-tile of `clas` (independent of the
+        // assignment) towards L2 while the assignment kernel drains, then wait for its matches / npos.
+        const float *first = P.clas + ((size_t)b * nvec + (size_t)cta0 + (size_t)tid * RN_LOSS_U) * V;
+        if (cta0 + tid * RN_LOSS_U < nvec) asm volatile("prefetch.global.L2 [%0];" ::"l"(first));
+        rn_pdl_wait();
+    }
 
     const int n_pos = P.npos[b];
     const float n_norm = fmaxf((float)n_pos, 1.0f);    // clamp(min=1), Vision.py:1530
@@ -359,6 +365,7 @@ rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ R
         }
     }
 
+    rn_pdl_trigger();  // the final-reduction kernel may be scheduled as the last CTAs retire
     // ---- block reduction (fixed order) -> one partial pair per CTA ----
     float c = rn_warp_sum(acc_neg + acc_pos);
     float r = rn_warp_sum(acc_reg);
@@ -388,6 +395,7 @@ rn_loss_final_kernel(const float2 *__restrict__ partials, const int32_t *__restr
                      float w_reg, float w_clas, float bs, float *__restrict__ per_image /*[B][2]*/,
                      float *__restrict__ out3) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    rn_pdl_wait();  // launched with PDL behind the loss kernel: its partials must be complete and visible
     for (int b = warp; b < B; b += nwarps) {
         double cs = 0.0, rs = 0.0;
         const float2 *p = partials + (size_t)b * tiles;
@@ -478,10 +486,10 @@ extern "C" size_t rn_loss_workspace_bytes(int B, int A, int C) {
 template <int V, int CVT, bool LOGITS>
 static void rn_launch_loss(bool g2, bool grad, dim3 grid, size_t smem, cudaStream_t s, const RnLossParams &P,
                            const RnGeom &g) {
-    if (g2 && grad) rn_loss_kernel<V, CVT, true, true, LOGITS><<<grid, RN_THREADS, smem, s>>>(P, g);
-    else if (g2) rn_loss_kernel<V, CVT, true, false, LOGITS><<<grid, RN_THREADS, smem, s>>>(P, g);
-    else if (grad) rn_loss_kernel<V, CVT, false, true, LOGITS><<<grid, RN_THREADS, smem, s>>>(P, g);
-    else rn_loss_kernel<V, CVT, false, false, LOGITS><<<grid, RN_THREADS, smem, s>>>(P, g);
+    if (g2 && grad) rn_launch_pdl(rn_loss_kernel<V, CVT, true, true, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
+    else if (g2) rn_launch_pdl(rn_loss_kernel<V, CVT, true, false, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
+    else if (grad) rn_launch_pdl(rn_loss_kernel<V, CVT, false, true, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
+    else rn_launch_pdl(rn_loss_kernel<V, CVT, false, false, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
 }
 
 static int rn_loss_impl(bool logits, float *probs, const float *clas, const float *reg, const float *gt_boxes,
@@ -568,8 +576,8 @@ static int rn_loss_impl(bool logits, float *probs, const float *clas, const floa
     }
     rc = rn_check_launch("rn_loss");
     if (rc) return rc;
-    rn_loss_final_kernel<<<1, 1024, 0, s>>>(reinterpret_cast<const float2 *>(P.partials), npos, B, tiles, w_reg,
-                                            w_clas, bs, per_image, out3);
+    rn_launch_pdl(rn_loss_final_kernel, dim3(1), dim3(1024), 0, s, reinterpret_cast<const float2 *>(P.partials), npos, B,
+                  tiles, w_reg, w_clas, bs, per_image, out3);
     return rn_check_launch("rn_loss_final");
 }
 
