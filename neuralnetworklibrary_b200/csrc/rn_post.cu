@@ -193,6 +193,7 @@ rn_post_scan_kernel(const float *__restrict__ clas, const float *__restrict__ re
             }
         }
     }
+    rn_pdl_trigger();  // the select kernel may be scheduled as this grid's last CTAs retire
     // ... and appended to the image's list with ONE global atomic per CTA (per-warp global atomics on a
     // single per-image counter serialised in L2 and held the first version to 27 % of DRAM peak).
     __syncthreads();
@@ -252,6 +253,8 @@ rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t
 
     const int b = blockIdx.x, tid = threadIdx.x;
     const unsigned long long *kb = keys + (size_t)b * cap;
+    rn_pdl_wait();     // launched with PDL behind the scan kernel
+    rn_pdl_trigger();  // the NMS kernel may become resident behind us; it waits for this grid to complete
     const int n = min(counts[b], cap);
     const int K = min(top_k, n);
     if (tid == 0) nsel[b] = K;
@@ -354,6 +357,8 @@ struct RnNmsParams {
     float *out_scores;
     int32_t *out_idx;
     int32_t *out_counts;
+    int32_t *out_ncand;           // optional copy of the candidate counts (what nms received)
+    const int32_t *cand_counts;
 };
 
 // The greedy loop of the reference (retinanet.py:590-602) keeps the best remaining box and deletes every
@@ -378,6 +383,7 @@ rn_post_nms_kernel(const __grid_constant__ RnNmsParams P, const __grid_constant_
     __shared__ int s_nk;
 
     const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    rn_pdl_wait();  // launched with PDL behind the select kernel
     const int K = P.nsel[b];
     const unsigned long long *sel = P.sel + (size_t)b * P.top_k;
     const bool pack = !FROM_BOXES && P.pack;
@@ -453,6 +459,7 @@ rn_post_nms_kernel(const __grid_constant__ RnNmsParams P, const __grid_constant_
     }
 
     if (tid == 0 && P.out_counts) P.out_counts[b] = nk;
+    if (tid == 0 && P.out_ncand) P.out_ncand[b] = P.cand_counts[b];
     for (int t = tid; t < nk; t += nthr) {
         const int i = s_keep[t];
         const unsigned long long key = sel[i];
@@ -494,25 +501,25 @@ extern "C" size_t rn_nms_workspace_bytes(int n, int top_k) {
 
 static int rn_launch_select_nms(bool from_boxes, int B, int cap, RnNmsParams &P, const RnGeom &g, const RnDecode &dec,
                                 unsigned char *ws, const RnPostWs &L, cudaStream_t s) {
-    rn_post_select_kernel<<<B, RN_SEL_THREADS, 0, s>>>(reinterpret_cast<unsigned long long *>(ws + L.keys),
-                                                       reinterpret_cast<int32_t *>(ws + L.counts), cap, P.top_k,
-                                                       reinterpret_cast<unsigned long long *>(ws + L.sel),
-                                                       reinterpret_cast<int32_t *>(ws + L.nsel));
+    rn_launch_pdl(rn_post_select_kernel, dim3(B), dim3(RN_SEL_THREADS), 0, s,
+                  reinterpret_cast<const unsigned long long *>(ws + L.keys), reinterpret_cast<const int32_t *>(ws + L.counts), cap,
+                  P.top_k, reinterpret_cast<unsigned long long *>(ws + L.sel), reinterpret_cast<int32_t *>(ws + L.nsel));
     int rc = rn_check_launch("rn_post_select");
     if (rc) return rc;
     P.sel = reinterpret_cast<unsigned long long *>(ws + L.sel);
     P.nsel = reinterpret_cast<int32_t *>(ws + L.nsel);
+    P.cand_counts = reinterpret_cast<const int32_t *>(ws + L.counts);
     const size_t smem = sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4 +
                         (size_t)P.top_k * (sizeof(float4) + sizeof(float) + 2 * sizeof(int));
     cudaError_t e;
     if (from_boxes) {
         e = cudaFuncSetAttribute(rn_post_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_nms smem: %s", cudaGetErrorString(e));
-        rn_post_nms_kernel<true><<<B, RN_SEL_THREADS, smem, s>>>(P, g, dec);
+        rn_launch_pdl(rn_post_nms_kernel<true>, dim3(B), dim3(RN_SEL_THREADS), smem, s, P, g, dec);
     } else {
         e = cudaFuncSetAttribute(rn_post_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_postproc smem: %s", cudaGetErrorString(e));
-        rn_post_nms_kernel<false><<<B, RN_SEL_THREADS, smem, s>>>(P, g, dec);
+        rn_launch_pdl(rn_post_nms_kernel<false>, dim3(B), dim3(RN_SEL_THREADS), smem, s, P, g, dec);
     }
     return rn_check_launch("rn_post_nms");
 }
@@ -574,14 +581,8 @@ extern "C" int rn_postproc(const float *clas, const float *reg, int B, int A, in
     P.clas = clas; P.reg = reg; P.table = table; P.A = A; P.C = C; P.pack = pack;
     P.top_k = top_k; P.max_keep = max_keep; P.max_overlap = max_overlap;
     P.out_boxes = reinterpret_cast<float4 *>(boxes); P.out_classes = classes; P.out_scores = scores;
-    P.out_idx = anchor_idx; P.out_counts = counts;
-    rc = rn_launch_select_nms(false, B, A, P, g, dec, ws, L, s);
-    if (rc) return rc;
-    if (n_candidates) {
-        e = cudaMemcpyAsync(n_candidates, d_counts, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToDevice, s);
-        if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_postproc copy: %s", cudaGetErrorString(e));
-    }
-    return RN_OK;
+    P.out_idx = anchor_idx; P.out_counts = counts; P.out_ncand = n_candidates;
+    return rn_launch_select_nms(false, B, A, P, g, dec, ws, L, s);
 }
 
 extern "C" int rn_nms(const float *boxes, const int64_t *classes, const float *scores, int n, float max_overlap,
