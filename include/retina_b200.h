@@ -94,7 +94,7 @@ int rn_loss(const float *clas, const float *reg, const float *gt_boxes, const in
             void *workspace, size_t workspace_bytes, void *stream);
 
 /* Same as rn_loss, but the class activations are LOGITS: the head's nn.Sigmoid (retinanet.py:258, :286) is
- * fused into the kernel (y = 1/(1+exp(-z)), accurate expf + IEEE divide as torch's CUDA sigmoid) and
+ * fused into the kernel (y = 1/(1+exp(-z)) within ~5 ulp of the correctly rounded value) and
  * dlogits = d loss / d logits (chained through sigmoid's backward, grad*(1-y)*y).  SURVEY.md section 8f row 1:
  * not a drop-in (ObjectDetectionNet.forward must return logits); it removes one full read+write pass over
  * [B,A,C] from the model's forward and one from its backward.  probs_out ([B,A,C], may be NULL) receives

@@ -66,9 +66,10 @@ __device__ __forceinline__ float rn_rcp_approx(float x) {
 }
 
 // LOGITS variant: the class activations are logits and the head's
-// nn.Sigmoid (reference retinanet.py:258,286) is fused here.  y = 1 / (1 + exp(-z)) with the accurate expf
-// and an IEEE divide -- the operations torch's CUDA sigmoid kernel performs -- and the gradient is chained
-// through sigmoid's backward, grad * (1 - y) * y.
+// nn.Sigmoid (reference retinanet.py:258,286) is fused here, y = 1 / (1 + exp(-z)), and the gradient is
+// chained through sigmoid's backward, grad * (1 - y) * y.  This scalar form (accurate expf + IEEE divide,
+// the operations of torch's CUDA sigmoid kernel) serves the C % 4 != 0 path; the vector path uses
+// rn_sigmoid_pair below.
 __device__ __forceinline__ float rn_sigmoid(float z) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-z))); }
 
 // One class element.  POS selects the target (t = 1 for the matched class of a positive anchor).
@@ -131,6 +132,32 @@ __device__ __forceinline__ rn_f2 rn_add2(rn_f2 a, rn_f2 b) {
     return r;
 }
 __device__ __forceinline__ rn_f2 rn_splat(float a) { return rn_pack(a, a); }
+
+// sigmoid of two logits, arithmetic packed two-wide: 2^(z * -log2 e) with the product's rounding error
+// carried in a correction term, MUFU.EX2, 1 + e, MUFU.RCP refined by one Newton step.  Within ~5 ulp of the
+// correctly rounded value (MUFU.EX2 itself is a 2-ulp approximation); ~5 issue slots per element instead of
+// the ~17 of expf + an IEEE divide.
+__device__ __forceinline__ void rn_sigmoid_pair(float z0, float z1, float &y0, float &y1) {
+    const rn_f2 z = rn_pack(z0, z1);
+    const rn_f2 c_hi = rn_splat(-1.4426950216293335f);       // float32(-log2 e)
+    const rn_f2 t_hi = rn_mul2(z, c_hi);
+    rn_f2 t_lo = rn_fma2(z, c_hi, t_hi ^ 0x8000000080000000ull);          // exact residual of the product
+    t_lo = rn_fma2(z, rn_splat(-1.925963033500011e-08f), t_lo);           // + z * (-log2 e - float32(-log2 e))
+    float a0, a1;
+    rn_unpack(t_hi, a0, a1);
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+    const rn_f2 eb = rn_pack(e0, e1);
+    const rn_f2 e = rn_fma2(rn_mul2(eb, rn_splat(0.6931471805599453f)), t_lo, eb);  // 2^(t_hi + t_lo)
+    const rn_f2 one = rn_splat(1.0f);
+    const rn_f2 d = rn_add2(e, one);
+    float d0, d1;
+    rn_unpack(d, d0, d1);
+    const rn_f2 r0 = rn_pack(rn_rcp_approx(d0), rn_rcp_approx(d1));
+    const rn_f2 err = rn_fma2(d ^ 0x8000000080000000ull, r0, one);       // 1 - d * r0
+    rn_unpack(rn_fma2(r0, err, r0), y0, y1);
+}
 
 // Two background (target 0) class elements with gamma == 2: same mathematics as
 // rn_focal_elem<false, true, GRAD>, arithmetic packed two-wide.  acc2 accumulates pw * (-2 log q).
@@ -221,8 +248,13 @@ __device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, const flo
         float part = 0.0f;
         RnVec<V> gv;
         float y[V];  // probabilities: the input itself, or sigmoid(logit)
+        if (LOGITS && V == 4) {
+            rn_sigmoid_pair(xv[u].at(0), xv[u].at(1), y[0], y[1]);
+            rn_sigmoid_pair(xv[u].at(2), xv[u].at(3), y[2 % V], y[3 % V]);
+        } else {
 #pragma unroll
-        for (int e = 0; e < V; ++e) y[e] = LOGITS ? rn_sigmoid(xv[u].at(e)) : xv[u].at(e);
+            for (int e = 0; e < V; ++e) y[e] = LOGITS ? rn_sigmoid(xv[u].at(e)) : xv[u].at(e);
+        }
         bool slow = false;
         int pe = -1;
         if (m >= 0) {  // rare: a positive anchor; is its class inside this vector?  (Vision.py:1588-1593)
