@@ -490,12 +490,12 @@ rn_scale_kernel(float *__restrict__ a, size_t na, float *__restrict__ bptr, size
 // C ABI
 // ------------------------------------------------------------------------------------------------
 // Sub-tiles per CTA: as many as possible (amortises the CTA prologue / reduction) while the grid still
-// has >= ~8 waves of 148 SMs x 3 resident CTAs.
+// has >= ~4 waves of 148 SMs x 3 resident CTAs (measured: Pascal B=32 is best with 2, COCO B=16 with 4).
 static int rn_loss_iters(int B, int A, int C) {
     const int V = (C % 4 == 0) ? 4 : 1;
     const long long sub = ((long long)A * (C / V) + RN_LOSS_TILE - 1) / RN_LOSS_TILE;
     int it = 4;
-    while (it > 1 && (long long)B * ((sub + it - 1) / it) < 8LL * 148 * 3) it >>= 1;
+    while (it > 1 && (long long)B * ((sub + it - 1) / it) < 4LL * 148 * 3) it >>= 1;
     return it;
 }
 static int rn_loss_tiles(int B, int A, int C) {  // CTAs (= partials) per image
