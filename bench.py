@@ -155,10 +155,31 @@ def time_loss_graph(anchors, sets, steps, warmup, device, world, from_logits=Fal
     loss_fn = SSD_loss(global_batch=sets[0][0].shape[0] * world, from_logits=from_logits)
     caps = [loss_fn.capture([anchors, reg, clas], [gb, gc]) for clas, reg, gb, gc in sets]
 
+    # The 12-byte loss exchange runs on its own stream: step k+1's kernels do not wait for step k's all-gather
+    # (nothing on the GPU consumes the summed loss).  Each captured step owns its out3 buffer, and a step
+    # waits for the exchange that last read that buffer before overwriting it.
+    comm = torch.cuda.Stream(device=device) if world > 1 else None
+    ready = [None] * len(caps)   # event: the exchange that read caps[i].out3 has finished
+    totals = [None] * len(caps)
+
     def step(k):
-        cap = caps[k % len(caps)]
+        i = k % len(caps)
+        cap = caps[i]
+        if world == 1:
+            cap.replay()
+            return cap.out3
+        main = torch.cuda.current_stream(device)
+        if ready[i] is not None:
+            main.wait_event(ready[i])
         cap.replay()
-        return reduce_loss_scalars(cap.out3) if world > 1 else cap.out3
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(comm):
+            comm.wait_event(done)
+            totals[i] = reduce_loss_scalars(cap.out3)
+            ready[i] = torch.cuda.Event()
+            ready[i].record(comm)
+        return totals[i]
 
     for k in range(warmup):
         step(k)
@@ -170,6 +191,8 @@ def time_loss_graph(anchors, sets, steps, warmup, device, world, from_logits=Fal
     t0.record()
     for k in range(steps):
         out3 = step(warmup + k)
+    if world > 1:
+        torch.cuda.current_stream(device).wait_stream(comm)   # the timed region ends when the last exchange has
     t1.record()
     torch.cuda.synchronize(device)
     if world > 1:
