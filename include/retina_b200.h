@@ -75,6 +75,15 @@ int rn_max_overlaps(const float *gt_boxes, const int64_t *gt_cats, int B, int M,
                     const double *base /*host*/, int K, const float *anchors /*or NULL*/, int A,
                     float *out, void *stream);
 
+/* The bounding-box half of AspectRatioCollater (Vision.py:770-785 scale + jitter, :798-809 -1 padding) from one
+ * ragged upload: boxes [N,4] float64 and cats [N] int64 are the images' boxes
+ * concatenated, offsets [B+1] int32 the image boundaries, scales [B] float64 the per-image resize factors (all
+ * DEVICE).  out_boxes [B,M,4] fp32 = float32((box*scale_b)*rand_scale + jitter), out_cats [B,M] int64, rows
+ * beyond an image's count are -1.  M = max(1, longest image). */
+int rn_stage_targets(const double *boxes, const int64_t *cats, const int32_t *offsets, const double *scales,
+                     double rand_scale, int row_jit, int col_jit, int B, int M, float *out_boxes,
+                     int64_t *out_cats, void *stream);
+
 /* Workspace for rn_loss (bytes; 256-byte aligned base required). */
 size_t rn_loss_workspace_bytes(int B, int A, int C);
 

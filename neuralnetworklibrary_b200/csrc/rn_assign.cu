@@ -272,6 +272,33 @@ rn_max_overlaps_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Target staging: the bounding-box half of AspectRatioCollater
+// (Vision.py:770-785 scale + jitter, :798-809 padding with -1), on the device from one ragged upload.
+// out[b, j] = float32((box * scale_b) * rand_scale + jitter) in float64 like NumPy, -1 beyond the image's count.
+__global__ void rn_stage_targets_kernel(const double *__restrict__ boxes, const int64_t *__restrict__ cats,
+                                        const int32_t *__restrict__ offsets, const double *__restrict__ scales,
+                                        double rand_scale, double row_jit, double col_jit, int B, int M,
+                                        float4 *__restrict__ out_boxes, int64_t *__restrict__ out_cats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * M) return;
+    const int b = i / M, j = i - b * M;
+    const int lo = offsets[b], n = offsets[b + 1] - lo;
+    float4 ob = make_float4(-1.f, -1.f, -1.f, -1.f);
+    long long oc = -1;
+    if (j < n) {
+        const double *src = boxes + 4 * (size_t)(lo + j);
+        const double sc = scales[b];
+        ob.x = __double2float_rn(__dadd_rn(__dmul_rn(__dmul_rn(src[0], sc), rand_scale), col_jit));
+        ob.y = __double2float_rn(__dadd_rn(__dmul_rn(__dmul_rn(src[1], sc), rand_scale), row_jit));
+        ob.z = __double2float_rn(__dadd_rn(__dmul_rn(__dmul_rn(src[2], sc), rand_scale), col_jit));
+        ob.w = __double2float_rn(__dadd_rn(__dmul_rn(__dmul_rn(src[3], sc), rand_scale), row_jit));
+        oc = cats[lo + j];
+    }
+    out_boxes[i] = ob;
+    out_cats[i] = oc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
 static const size_t kBaseBytes = sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4;
@@ -339,4 +366,17 @@ extern "C" int rn_max_overlaps(const float *gt_boxes, const int64_t *gt_cats, in
     rn_max_overlaps_kernel<<<grid, RN_THREADS, smem, s>>>(reinterpret_cast<const float4 *>(gt_boxes), gt_cats, M, g,
                                                           reinterpret_cast<const float4 *>(anchors), out);
     return rn_check_launch("rn_max_overlaps");
+}
+
+extern "C" int rn_stage_targets(const double *boxes, const int64_t *cats, const int32_t *offsets, const double *scales,
+                                double rand_scale, int row_jit, int col_jit, int B, int M, float *out_boxes,
+                                int64_t *out_cats, void *stream) {
+    if (B <= 0 || M <= 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_stage_targets: B=%d M=%d", B, M);
+    if (!offsets || !scales || !out_boxes || !out_cats) return rn_set_error(RN_ERR_INVALID_ARG, "rn_stage_targets: null pointer");
+    if (((uintptr_t)out_boxes) & 15) return rn_set_error(RN_ERR_INVALID_ARG, "rn_stage_targets: out_boxes must be 16-byte aligned");
+    const int n = B * M;
+    rn_stage_targets_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        boxes, cats, offsets, scales, rand_scale, (double)row_jit, (double)col_jit, B, M,
+        reinterpret_cast<float4 *>(out_boxes), out_cats);
+    return rn_check_launch("rn_stage_targets");
 }

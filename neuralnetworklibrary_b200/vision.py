@@ -321,3 +321,62 @@ class ComputeMaxOverlaps(object):
             self.max_overlaps += list(v)
             means.append(v.mean())
         return TEN(float(np.array(means).mean()) if means else 0.0)
+
+
+def stage_targets(bboxes, cats, scales, rand_scale=1.0, row_jit=0, col_jit=0, device=None):
+    """Device-side version of the target half of AspectRatioCollater (reference Vision.py:770-785, :798-812):
+    per-image box arrays are rescaled (box * scale_i * rand_scale), shifted by the jitter, rounded to float32
+    and padded with -1 to the longest image -- from ONE pinned, ragged host->device upload and one small kernel
+    instead of a padded host array per batch.  Returns [BBoxes (bs x M x 4) float32, Cats (bs x M) int64] on
+    the device, ready for SSD_loss.  Arithmetic is float64 like NumPy's for integer / float64 box arrays."""
+    lib = _lib.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    B = len(bboxes)
+    counts = [0 if b is None else len(b) for b in bboxes]
+    M = max(1, max(counts) if counts else 1)
+    N = sum(counts)
+    offsets = np.zeros(B + 1, dtype=np.int32)
+    offsets[1:] = np.cumsum(counts)
+    # one pinned staging buffer: boxes f64 [N,4] | cats i64 [N] | scales f64 [B] | offsets i32 [B+1]
+    nb, nc, ns, no = 32 * N, 8 * N, 8 * B, 4 * (B + 1)
+    host = torch.empty(nb + nc + ns + no + 8, dtype=torch.uint8, pin_memory=True)
+    hv = host.numpy()
+    hb, hc = hv[:nb].view(np.float64).reshape(N, 4), hv[nb:nb + nc].view(np.int64)
+    for i, (b, c) in enumerate(zip(bboxes, cats)):
+        if counts[i]:
+            hb[offsets[i]:offsets[i + 1]] = np.asarray(b, dtype=np.float64).reshape(-1, 4)
+            hc[offsets[i]:offsets[i + 1]] = np.asarray(c, dtype=np.int64).reshape(-1)
+    hv[nb + nc:nb + nc + ns].view(np.float64)[:] = np.asarray(scales, dtype=np.float64)
+    hv[nb + nc + ns:nb + nc + ns + no].view(np.int32)[:] = offsets
+    with torch.cuda.device(device):
+        dev_buf = host.to(device, non_blocking=True)
+        out_boxes = torch.empty((B, M, 4), dtype=torch.float32, device=device)
+        out_cats = torch.empty((B, M), dtype=torch.int64, device=device)
+        p = dev_buf.data_ptr()
+        import ctypes as C
+        _lib.check(lib.rn_stage_targets(C.c_void_p(p), C.c_void_p(p + nb), C.c_void_p(p + nb + nc + ns), C.c_void_p(p + nb + nc),
+                                        float(rand_scale), int(row_jit), int(col_jit), B, M, _lib.ptr(out_boxes),
+                                        _lib.ptr(out_cats), _lib.stream_ptr(device)))
+        dev_buf.record_stream(torch.cuda.current_stream(device))
+    return [out_boxes, out_cats]
+
+
+def merge_tta_predictions(passes, max_overlap=0.5, rel_thresh=None, top_k=1000, max_boxes=20, dup=None, inc=None):
+    """The merge step of ImageLearner.TTA_bbox (reference Vision.py:2104-2119): `passes` is a list (one entry per
+    augmentation pass) of per-image [boxes, classes, scores] lists already mapped back to the original image; the
+    passes' predictions of each image are concatenated and nms() (GPU) is applied to the union."""
+    from .retinanet import nms
+    L = len(passes[0])
+    merged = []
+    for l in range(L):
+        boxes, classes, scores = [], [], []
+        for p in passes:
+            boxes += list(p[l][0])
+            classes += list(p[l][1])
+            scores += list(p[l][2])
+        if len(boxes) == 0:
+            merged.append([[], [], []])
+            continue
+        merged.append(list(nms(TEN(boxes), TEN([int(c) for c in classes]), TEN([float(v) for v in scores]), max_overlap,
+                               rel_thresh, top_k, max_boxes, dup, inc)))
+    return merged

@@ -191,3 +191,28 @@ def decode_one(anchor, reg, mean, std, img_h, img_w):
     lib().orc_decode_one(_ptr(a, _f32p), _ptr(r, _f32p), _ptr(m, _f32p), _ptr(s, _f32p), int(img_h),
                          int(img_w), _ptr(out, _f32p))
     return out
+
+
+def stage_targets(bboxes, cats, scales, rand_scale=1.0, row_jit=0, col_jit=0):
+    """numpy restatement of the target half of AspectRatioCollater (reference Vision.py:770-785 scale + jitter,
+    :798-809 padding with -1).  Returns (bboxes_padded [bs,M,4] float32, cats_padded [bs,M] int64)."""
+    bs = len(bboxes)
+    out = []
+    for i in range(bs):
+        b = np.asarray(bboxes[i])
+        if len(b) > 0:
+            b = b * scales[i] * rand_scale                                        # Vision.py:773
+            b = np.array([b[:, 0] + col_jit, b[:, 1] + row_jit, b[:, 2] + col_jit, b[:, 3] + row_jit]).T  # :783-784
+        out.append(b)
+    M = max([len(b) for b in out]) if bs else 0
+    if M > 0:                                                                     # Vision.py:799-806
+        bp = np.ones((bs, M, 4)).astype(np.float32) * (-1)
+        cp = np.ones((bs, M)).astype(np.int64) * (-1)
+        for i, (b, c) in enumerate(zip(out, cats)):
+            if len(b) > 0:
+                bp[i, :len(b), :] = b
+                cp[i, :len(c)] = c
+    else:                                                                         # Vision.py:807-809
+        bp = np.ones((bs, 1, 4)).astype(np.float32) * (-1)
+        cp = np.ones((bs, 1)).astype(np.int64) * (-1)
+    return bp, cp

@@ -158,6 +158,41 @@ def gen_nms_boxes():
     np.savez_compressed(os.path.join(OUT, "nms_boxes.npz"), **d)
 
 
+def collater_cases():
+    """Ragged ground truth for the collater fixture: (boxes int64 / float64, cats) per image, incl. empty images."""
+    rng = np.random.RandomState(77)
+    cases = []
+    for bs, empty_all in ((4, False), (3, True), (5, False)):
+        boxes, cats, scales = [], [], []
+        for i in range(bs):
+            n = 0 if (empty_all or i == 1) else int(rng.randint(1, 9))
+            xy = rng.randint(0, 200, size=(n, 2))
+            wh = rng.randint(5, 120, size=(n, 2))
+            b = np.concatenate([xy, xy + wh], axis=1)
+            boxes.append(b.astype(np.float64) if i % 2 else b.astype(np.int64))
+            cats.append(rng.randint(0, 20, size=n).astype(np.int64))
+            scales.append(float(rng.uniform(0.5, 2.0)))
+        cases.append((boxes, cats, scales, float(rng.uniform(0.8, 1.25)), int(rng.randint(0, 17)), int(rng.randint(0, 17))))
+    return cases
+
+
+def gen_collater():
+    """Target half of the reference's AspectRatioCollater (Vision.py:730-812) on tiny synthetic images."""
+    from oracle import ref_shim
+    _, vis = ref_shim.load()
+    d = {}
+    for k, (boxes, cats, scales, rand_scale, row_jit, col_jit) in enumerate(collater_cases()):
+        batch = []
+        for i in range(len(boxes)):
+            img = np.zeros((8, 8, 3), dtype=np.float32)
+            b = boxes[i].copy() if len(boxes[i]) else np.array([])
+            batch.append((img, scales[i], rand_scale, row_jit, col_jit, b, cats[i].copy() if len(cats[i]) else np.array([])))
+        _, (bp, cp) = vis.AspectRatioCollater(batch)
+        d["case%d_boxes" % k] = bp.numpy()
+        d["case%d_cats" % k] = cp.numpy()
+    np.savez_compressed(os.path.join(OUT, "collater_targets.npz"), **d)
+
+
 if __name__ == "__main__":
     if not ref.available():
         sys.exit("reference checkout not found; golden fixtures can only be regenerated where it exists")
@@ -166,6 +201,7 @@ if __name__ == "__main__":
     gen_loss_cfg1()
     gen_postproc_small()
     gen_nms_boxes()
+    gen_collater()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
