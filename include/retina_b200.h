@@ -147,6 +147,15 @@ int rn_nms(const float *boxes, const int64_t *classes, const float *scores, int 
            int top_k, int max_keep, int32_t *keep_idx, int32_t *count, void *workspace,
            size_t workspace_bytes, void *stream);
 
+/* The per-image matching of mAP1 (Vision.py:1716-1727) for a whole validation set.
+ * Predictions and ground-truth boxes of all images are concatenated: pred_boxes [NP,4] fp32, pred_cls [NP] int32,
+ * pred_off [N+1] int32 (image boundaries); targ_boxes [NT,4] fp32, targ_cls [NT] int32, targ_img [NT] int32 (image of
+ * each box); thresholds [T] fp32 (all DEVICE).  is_correct [T][NP] uint8 is cleared and then set to 1 where a
+ * ground-truth box's best same-category prediction (first maximal IoU) exceeds the threshold. */
+int rn_map_match(const float *pred_boxes, const int32_t *pred_cls, const int32_t *pred_off, const float *targ_boxes,
+                 const int32_t *targ_cls, const int32_t *targ_img, int NT, int NP, const float *thresholds, int T,
+                 unsigned char *is_correct, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -619,3 +619,64 @@ extern "C" int rn_nms(const float *boxes, const int64_t *classes, const float *s
     P.out_idx = keep_idx; P.out_counts = count;
     return rn_launch_select_nms(true, 1, n, P, g, dec, ws, L, s);
 }
+
+// ------------------------------------------------------------------------------------------------
+// mAP matching: the per-image part of mAP1 (Vision.py:1716-1727) for every
+// image, category and threshold of a validation set in one launch.  One thread per ground-truth box: among
+// the image's predictions of the box's category (in prediction order) find the first maximal IoU
+// (jaccard(targets, preds).max(dim=1), fp32, targets as Boxes1) and flag that prediction as correct for every
+// threshold the IoU exceeds (strict >).  Several boxes may flag the same prediction; the store is idempotent.
+// ------------------------------------------------------------------------------------------------
+__global__ void rn_map_match_kernel(const float4 *__restrict__ pred_boxes, const int32_t *__restrict__ pred_cls,
+                                    const int32_t *__restrict__ pred_off, const float4 *__restrict__ targ_boxes,
+                                    const int32_t *__restrict__ targ_cls, const int32_t *__restrict__ targ_img, int NT,
+                                    int NP, const float *__restrict__ thresholds, int T,
+                                    unsigned char *__restrict__ is_correct /*[T][NP]*/) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= NT) return;
+    const float4 tb = targ_boxes[j];
+    const float ta = rn_area(tb);
+    const int c = targ_cls[j], img = targ_img[j];
+    const int lo = pred_off[img], hi = pred_off[img + 1];
+    float best = -INFINITY;
+    int bi = -1;
+    for (int p = lo; p < hi; ++p) {
+        if (pred_cls[p] != c) continue;
+        const float4 pb = pred_boxes[p];
+        // Vision.jaccard(targets, preds): intersection clamped at 0, union (a_t + a_p) - inter, IEEE divide
+        float iw = __fsub_rn(fminf(tb.z, pb.z), fmaxf(tb.x, pb.x));
+        float ih = __fsub_rn(fminf(tb.w, pb.w), fmaxf(tb.y, pb.y));
+        iw = iw > 0.0f ? iw : 0.0f;
+        ih = ih > 0.0f ? ih : 0.0f;
+        const float inter = __fmul_rn(iw, ih);
+        const float v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ta, rn_area(pb)), inter));
+        if (bi < 0 || v > best) {  // first maximal index
+            best = v;
+            bi = p;
+        }
+    }
+    if (bi < 0) return;  // no prediction of this category in the image
+    for (int t = 0; t < T; ++t)
+        if (best > thresholds[t]) is_correct[(size_t)t * NP + bi] = 1;
+}
+
+extern "C" int rn_map_match(const float *pred_boxes, const int32_t *pred_cls, const int32_t *pred_off,
+                            const float *targ_boxes, const int32_t *targ_cls, const int32_t *targ_img, int NT, int NP,
+                            const float *thresholds, int T, unsigned char *is_correct, void *stream) {
+    if (NT < 0 || NP < 0 || T <= 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_map_match: NT=%d NP=%d T=%d", NT, NP, T);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (NP > 0) {
+        if (!is_correct) return rn_set_error(RN_ERR_INVALID_ARG, "rn_map_match: null output");
+        cudaError_t e = cudaMemsetAsync(is_correct, 0, (size_t)T * NP, s);
+        if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_map_match memset: %s", cudaGetErrorString(e));
+    }
+    if (NT == 0 || NP == 0) return RN_OK;
+    if (!pred_boxes || !pred_cls || !pred_off || !targ_boxes || !targ_cls || !targ_img || !thresholds)
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_map_match: null pointer");
+    if ((((uintptr_t)pred_boxes) | ((uintptr_t)targ_boxes)) & 15)
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_map_match: boxes must be 16-byte aligned");
+    rn_map_match_kernel<<<(NT + 127) / 128, 128, 0, s>>>(reinterpret_cast<const float4 *>(pred_boxes), pred_cls, pred_off,
+                                                         reinterpret_cast<const float4 *>(targ_boxes), targ_cls, targ_img, NT,
+                                                         NP, thresholds, T, is_correct);
+    return rn_check_launch("rn_map_match");
+}

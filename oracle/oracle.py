@@ -216,3 +216,46 @@ def stage_targets(bboxes, cats, scales, rand_scale=1.0, row_jit=0, col_jit=0):
         bp = np.ones((bs, 1, 4)).astype(np.float32) * (-1)
         cp = np.ones((bs, 1)).astype(np.int64) * (-1)
     return bp, cp
+
+
+def jaccard_f32(a, b):
+    """Vision.jaccard (reference Vision.py:234-256) in numpy float32: [n,4] x [m,4] -> [n,m]."""
+    a, b = _f32(a).reshape(-1, 4), _f32(b).reshape(-1, 4)
+    area_a = ((a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1]))[:, None]
+    area_b = ((b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1]))[None, :]
+    iw = np.clip(np.minimum(a[:, None, 2], b[None, :, 2]) - np.maximum(a[:, None, 0], b[None, :, 0]), 0, None)
+    ih = np.clip(np.minimum(a[:, None, 3], b[None, :, 3]) - np.maximum(a[:, None, 1], b[None, :, 1]), 0, None)
+    inter = (iw * ih).astype(np.float32)
+    return inter / ((area_a + area_b) - inter)
+
+
+def map_table(predictions, targets, C, thresholds):
+    """numpy restatement of mAP / mAP1 (reference Vision.py:1696-1800): the [len(thresholds), C] table of
+    per-(threshold, category) average precisions whose mean the reference returns."""
+    N = len(predictions)
+    table = np.zeros((len(thresholds), C))
+    for c in range(C):
+        targs = [[b for b, cc in targets[i] if cc == c] for i in range(N)]                       # Vision.py:1781-1789
+        sel = [[j for j in range(len(predictions[i][0])) if predictions[i][1][j] == c] for i in range(N)]
+        for t, thresh in enumerate(thresholds):
+            is_correct, scores = [], []
+            for i in range(N):                                                                   # Vision.py:1720-1727
+                ic = [0] * len(sel[i])
+                if len(sel[i]) > 0 and len(targs[i]) > 0:
+                    jac = jaccard_f32(np.array(targs[i]), np.array([predictions[i][0][j] for j in sel[i]]))
+                    for j in range(jac.shape[0]):
+                        idx = int(np.argmax(jac[j]))          # first maximal index, as torch.max(dim=1)
+                        if jac[j, idx] > np.float32(thresh):  # fp32 tensor vs python float compares in fp32
+                            ic[idx] = 1
+                is_correct += ic
+                scores += [predictions[i][2][j] for j in sel[i]]
+            pairs = sorted(zip(scores, is_correct), reverse=True)                                # Vision.py:1730-1731
+            ic_sorted = np.array([ic for _, ic in pairs])
+            L = len(ic_sorted)
+            ntrue = sum(len(x) for x in targs)
+            tp = np.cumsum(ic_sorted)
+            prec = tp * np.array([1 / n for n in range(1, L + 1)])
+            prec_max = np.flip(np.maximum.accumulate(np.flip(prec)))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                table[t, c] = np.sum(prec_max[ic_sorted.nonzero()[0]]) / np.float64(ntrue)       # Vision.py:1741-1747
+    return table

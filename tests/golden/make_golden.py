@@ -193,6 +193,69 @@ def gen_collater():
     np.savez_compressed(os.path.join(OUT, "collater_targets.npz"), **d)
 
 
+def map_cases():
+    """Validation-set predictions / targets for the mAP fixture: jittered copies of the ground truth plus random
+    boxes; images without predictions or without targets; exact duplicates (first-argmax tie) and tied scores."""
+    rng = np.random.RandomState(91)
+    cases = []
+    for N, C, holes in ((12, 4, False), (9, 5, True), (30, 3, False)):
+        predictions, targets = [], []
+        for i in range(N):
+            nt = 0 if (holes and i % 4 == 1) else int(rng.randint(1, 7))
+            xy = rng.uniform(0, 300, size=(nt, 2))
+            wh = rng.uniform(20, 150, size=(nt, 2))
+            tb = np.concatenate([xy, xy + wh], axis=1)
+            tc = rng.randint(0, C - 1 if holes else C, size=nt)   # holes: the last category has no ground truth
+            targets.append([(tb[j].copy(), int(tc[j])) for j in range(nt)])
+            pb, pc, ps = [], [], []
+            if not (holes and i % 4 == 2):
+                for j in range(nt):
+                    for _ in range(int(rng.randint(0, 4))):
+                        pb.append((tb[j] + rng.normal(0, 6, size=4)).astype(np.float32))
+                        pc.append(np.int64(tc[j] if rng.rand() < 0.8 else rng.randint(0, C)))
+                        ps.append(np.float32(rng.uniform(0.05, 1.0)))
+                for _ in range(int(rng.randint(0, 5))):
+                    q = rng.uniform(0, 300, size=2)
+                    pb.append(np.concatenate([q, q + rng.uniform(20, 150, size=2)]).astype(np.float32))
+                    pc.append(np.int64(rng.randint(0, C)))
+                    ps.append(np.float32(rng.uniform(0.05, 0.6)))
+                if len(pb) >= 2 and i % 3 == 0:
+                    pb.append(pb[0].copy()); pc.append(pc[0]); ps.append(ps[1])   # duplicate box, tied score
+            predictions.append([pb, pc, ps])
+        cases.append((predictions, targets, {c: "cat%d" % c for c in range(C)}))
+    return cases
+
+
+def gen_map():
+    """mAP1 / mAP (Vision.py:1696-1800) of the unmodified reference on map_cases()."""
+    import contextlib
+    import io
+    import warnings
+    from oracle import ref_shim
+    _, vis = ref_shim.load()
+    d = {}
+    for k, (predictions, targets, categories) in enumerate(map_cases()):
+        for name, thresholds in (("coco", vis.COCO_thresholds), ("pascal", vis.Pascal_thresholds), ("odd", [0.3, 0.62])):
+            N, C = len(predictions), len(categories)
+            table = np.zeros((len(thresholds), C))
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                for c in range(C):
+                    targs = [[b for b, cc in targets[i] if cc == c] for i in range(N)]
+                    preds = [[predictions[i][0][j] for j in range(len(predictions[i][0])) if predictions[i][1][j] == c]
+                             for i in range(N)]
+                    scores = [[predictions[i][2][j] for j in range(len(predictions[i][0])) if predictions[i][1][j] == c]
+                              for i in range(N)]
+                    for j, t in enumerate(thresholds):
+                        table[j, c] = vis.mAP1(targs, preds, scores, t)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    mean = vis.mAP(predictions, targets, categories, thresholds)
+            assert np.array_equal(np.float64(mean), np.mean(table), equal_nan=True)
+            d["case%d_%s_table" % (k, name)] = table
+            d["case%d_%s_mean" % (k, name)] = np.float64(mean)
+    np.savez_compressed(os.path.join(OUT, "map_scores.npz"), **d)
+
+
 if __name__ == "__main__":
     if not ref.available():
         sys.exit("reference checkout not found; golden fixtures can only be regenerated where it exists")
@@ -202,6 +265,7 @@ if __name__ == "__main__":
     gen_postproc_small()
     gen_nms_boxes()
     gen_collater()
+    gen_map()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
