@@ -114,6 +114,25 @@ int rn_loss_logits(const float *logits, const float *reg, const float *gt_boxes,
                    double gamma, double beta, int B_global, float *dlogits, float *dreg, float *probs_out,
                    float *out3, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Workspace for rn_loss_levels (bytes; 256-byte aligned base required). */
+size_t rn_loss_levels_workspace_bytes(int B, int H, int W, int K, int C);
+
+/* rn_loss / rn_loss_logits on the heads' NCHW level tensors as the convolutions produce them, i.e. WITHOUT the
+ * permute(0,2,3,1).contiguous().view() of retinanet.py:215-217, :289-295 and the torch.cat of Vision.py:1467-1468
+ * (removes two more read+write passes over [B,A,C] from the model's forward and two from
+ * its backward).  clas_levels / reg_levels / dclas_levels / dreg_levels / probs_levels are HOST arrays of
+ * RN_NUM_LEVELS device pointers (P3..P7): clas_l [B, K*C, gh_l, gw_l] fp32 with channel = k*C + c, reg_l
+ * [B, K*4, gh_l, gw_l] with channel = k*4 + j, gh_l = ceil(H/2^l), gw_l = ceil(W/2^l); gradients and probs_out have
+ * the layout of their inputs.  from_logits != 0: the class tensors hold logits (sigmoid fused, see rn_loss_logits).
+ * matches / npos come from rn_assign with anchors == NULL (generated anchors; anchor a = off_l + (iy*gw_l+ix)*K + k).
+ * Same value, gradients and out3 as rn_loss on the permuted + concatenated tensors (summation order differs). */
+int rn_loss_levels(const float *const *clas_levels /*host[5]*/, const float *const *reg_levels /*host[5]*/,
+                   int from_logits, const float *gt_boxes, const int64_t *gt_cats, const int32_t *matches,
+                   const int32_t *npos, int B, int C, int M, int H, int W, const double *base /*host*/, int K,
+                   double alpha, double gamma, double beta, int B_global, float *const *dclas_levels /*host[5] or NULL*/,
+                   float *const *dreg_levels /*host[5] or NULL*/, float *const *probs_levels /*host[5] or NULL*/,
+                   float *out3, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Backward with a non-unit upstream gradient: scales dclas[n_clas], dreg[n_reg] in place by the
  * DEVICE scalar *grad_out; the kernel exits immediately when *grad_out == 1 (what loss.backward()
  * passes, General/Learner.py:514), so the common case costs one empty launch and no host sync. */

@@ -16,7 +16,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 # RETINA_B200_LIB overrides the library path (A/B comparisons of builds); the default is the in-tree build.
 LIB_PATH = os.environ.get("RETINA_B200_LIB") or os.path.join(_PKG, "libretina_sm100.so")
-SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_post.cu"]
+SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_loss_levels.cu", "rn_post.cu"]
+BUILD_DIR = os.path.join(_PKG, "csrc", "_build")   # object files (git-ignored); the .so is what travels
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -24,45 +25,69 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-fmad=false",  # never contract a*b+c behind our back; fused ops are spelled fmaf() explicitly
     "-split-compile", "0",  # build-time only: ptxas works on the kernels of a translation unit in parallel
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 RN_OK, RN_ERR_INVALID_ARG, RN_ERR_WORKSPACE, RN_ERR_CUDA = 0, 1, 2, 3
 MATCH_NEG, MATCH_IGNORE = -1, -2
 MAX_TOP_K = 4096
 MAX_K = 16
+NUM_LEVELS = 5
 
 
 class RetinaB200Error(RuntimeError):
     pass
 
 
-def _stale():
-    if not os.path.exists(LIB_PATH):
+def _headers():
+    return glob.glob(os.path.join(_PKG, "csrc", "*.cuh")) + [os.path.join(_ROOT, "include", "retina_b200.h")]
+
+
+def _newer(deps, target):
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(_PKG, "csrc", s) for s in SOURCES] + glob.glob(os.path.join(_PKG, "csrc", "*.cuh")) + \
-        [os.path.join(_ROOT, "include", "retina_b200.h")]
+    t = os.path.getmtime(target)
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
+def _stale():
+    return _newer([os.path.join(_PKG, "csrc", s) for s in SOURCES] + _headers(), LIB_PATH)
+
+
 def build_library(force=False, verbose=False):
-    """Compiles every CUDA source of the package for sm_100a into LIB_PATH (cross-compiles without a GPU)."""
+    """Compiles every CUDA source of the package for sm_100a (one nvcc process per translation unit, in
+    parallel; cross-compiles without a GPU) and links LIB_PATH."""
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH] + [os.path.join(_PKG, "csrc", s) for s in SOURCES]
-    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    jobs = []
+    for src in SOURCES:
+        path = os.path.join(_PKG, "csrc", src)
+        obj = os.path.join(BUILD_DIR, src[:-3] + ".o")
+        if force or _newer([path] + _headers(), obj):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, path]
+            jobs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, proc in jobs:
+        out, _ = proc.communicate()
+        if proc.returncode != 0:
+            for _, other in jobs:
+                if other.poll() is None:
+                    other.kill()
+            raise RetinaB200Error("nvcc failed on %s:\n%s" % (src, out))
+        if verbose:
+            print(out)
+    objs = [os.path.join(BUILD_DIR, s[:-3] + ".o") for s in SOURCES]
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
-        raise RetinaB200Error("nvcc failed:\n" + res.stdout)
-    if verbose:
-        print(res.stdout)
+        raise RetinaB200Error("link failed:\n" + res.stdout)
     return LIB_PATH
 
 
 _vp, _f32p, _f64p, _i32p, _i64p = C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p
 _hf32p = C.POINTER(C.c_float)
+_pp = C.POINTER(C.c_void_p)   # host array of device pointers
 
 # name -> (restype, argtypes).  Mirrors include/retina_b200.h one to one (tests check the symbols).
 PROTOTYPES = {
@@ -87,6 +112,10 @@ PROTOTYPES = {
     "rn_postproc": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _f32p,
                               _hf32p, _hf32p, C.c_float, C.c_float, C.c_int, C.c_int, _f32p, _i64p, _f32p,
                               _i32p, _i32p, _i32p, _vp, C.c_size_t, _vp]),
+    "rn_loss_levels_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "rn_loss_levels": (C.c_int, [_pp, _pp, C.c_int, _f32p, _i64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 _f64p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, _pp, _pp, _pp, _f32p, _vp,
+                                 C.c_size_t, _vp]),
     "rn_map_match": (C.c_int, [_f32p, _i32p, _i32p, _f32p, _i32p, _i32p, C.c_int, C.c_int, _f32p, C.c_int, _vp, _vp]),
     "rn_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "rn_nms": (C.c_int, [_f32p, _i64p, _f32p, C.c_int, C.c_float, C.c_int, C.c_int, _i32p, _i32p, _vp,
@@ -128,6 +157,13 @@ def check(rc):
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def ptr_array(tensors):
+    """Host array of the tensors' device pointers (None -> NULL array)."""
+    if tensors is None:
+        return None
+    return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
 def stream_ptr(device=None):

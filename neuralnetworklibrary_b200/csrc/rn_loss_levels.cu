@@ -1,0 +1,491 @@
+// rn_loss_levels.cu -- the loss forward+backward of rn_loss.cu, reading the heads' NCHW level tensors directly
+// (second half).
+//
+// The reference's heads end with  out.permute(0,2,3,1).contiguous().view(B,-1,4|C)  (retinanet.py:215-217,
+// :289-295) and the model concatenates the five levels (Vision.py:1467-1468): one read+write pass over [B,A,C]
+// for the permute and one for the cat, and the same again for their backward.  This kernel consumes the conv
+// outputs as they are -- level l: clas_l [B, K*C, gh_l, gw_l], reg_l [B, K*4, gh_l, gw_l], channel = k*C + c
+// resp. k*4 + j -- and writes the gradients in the same layout, so those passes disappear from the model.
+//
+// Data movement.  Anchor row (level l, cell p = iy*gw+ix, slot k) is a = off_l + p*K + k; its class c lives at
+// clas_l[((b*K + k)*C + c)*P_l + p], P_l = gh_l*gw_l.  A thread owns V consecutive cells of one (b, k) -- V = the
+// largest of {4, 2, 1} dividing P_l, so every plane base stays V*4-byte aligned -- reads their V assignments once
+// (a stride-K gather from `matches`, amortised over all classes) and then walks the class planes with 8
+// independent V*4-byte loads in flight, exactly the element math of rn_loss.cu, V*4-byte streaming stores for the
+// gradient.  A warp therefore reads/writes 32*V*4 contiguous bytes per plane.  Algorithmic bytes are unchanged:
+// 8*A*(C+4) per image with gradients.  No tensor cores: there is no contraction on this path.
+#include "rn_loss_math.cuh"
+
+#define RN_LVL_U 8  // class planes in flight per thread
+
+struct RnLvlParams {
+    const float *clas[RN_NUM_LEVELS];
+    const float *reg[RN_NUM_LEVELS];
+    float *dclas[RN_NUM_LEVELS];
+    float *dreg[RN_NUM_LEVELS];
+    float *probs[RN_NUM_LEVELS];  // LOGITS only, may be NULL
+    const float4 *gt_boxes;
+    const int64_t *gt_cats;
+    const int32_t *matches;
+    const int32_t *npos;
+    float *partials;  // [B][grid.x][2]
+    int B, A, C, M, K;
+    int P[RN_NUM_LEVELS];         // cells per level
+    int V[RN_NUM_LEVELS];         // cells per thread (4, 2 or 1)
+    int tile0[RN_NUM_LEVELS + 1]; // first row-tile of each level in the per-image tile list
+    int cchunk, nchunks;          // classes per CTA, chunks per row-tile
+    float a_pos, a_neg, gamma, lo, hi;
+    float wc_over_bs, wr_over_bs;
+};
+
+template <int V>
+struct RnLv;
+template <>
+struct RnLv<4> {
+    float4 d;
+    __device__ __forceinline__ void load(const float *p) { d = rn_ldg_stream(reinterpret_cast<const float4 *>(p)); }
+    __device__ __forceinline__ void store(float *p) const { rn_stg_stream(reinterpret_cast<float4 *>(p), d); }
+    __device__ __forceinline__ float &at(int e) { return e == 0 ? d.x : (e == 1 ? d.y : (e == 2 ? d.z : d.w)); }
+};
+template <>
+struct RnLv<2> {
+    float2 d;
+    __device__ __forceinline__ void load(const float *p) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(d.x), "=f"(d.y) : "l"(p));
+    }
+    __device__ __forceinline__ void store(float *p) const {
+        asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(d.x), "f"(d.y) : "memory");
+    }
+    __device__ __forceinline__ float &at(int e) { return e == 0 ? d.x : d.y; }
+};
+template <>
+struct RnLv<1> {
+    float d;
+    __device__ __forceinline__ void load(const float *p) {
+        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(d) : "l"(p));
+    }
+    __device__ __forceinline__ void store(float *p) const { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(d) : "memory"); }
+    __device__ __forceinline__ float &at(int) { return d; }
+};
+
+// One class element with a run-time target (the rare blocks that contain a positive anchor's class).
+template <bool G2, bool GRAD>
+__device__ __forceinline__ float rn_focal_elem_rt(bool pos, float x, const RnLvlParams &P, float ga_neg, float ga_pos,
+                                                  float &acc_neg, float &acc_pos) {
+    float t = 0.0f, g;
+    if (pos) {
+        g = rn_focal_elem<true, G2, GRAD>(x, P.lo, P.hi, P.gamma, ga_pos, t);
+        acc_pos = fmaf(0.5f * P.a_pos, t, acc_pos);
+    } else {
+        g = rn_focal_elem<false, G2, GRAD>(x, P.lo, P.hi, P.gamma, ga_neg, t);
+        acc_neg += t;
+    }
+    return g;
+}
+
+// The work of one thread: V cells of one (image, level, slot), classes [c_begin, c_end).
+template <int V, bool G2, bool GRAD, bool LOGITS>
+__device__ __forceinline__ void rn_lvl_body(const RnLvlParams &P, const RnGeom &g, int b, int l, int row_tile, int chunk,
+                                            const float4 *s_box, const int *s_cat, float gl, int n_pos, float &acc_neg_w,
+                                            float &acc_pos, float &acc_reg) {
+    constexpr int NPK = (V >= 2) ? V / 2 : 1;  // packed accumulators
+    const int Pl = P.P[l], K = P.K, C = P.C;
+    const int rows = K * Pl;
+    const int r0 = (row_tile * RN_THREADS + threadIdx.x) * V;
+    if (r0 >= rows) return;
+    const int k = r0 / Pl;
+    const int p = r0 - k * Pl;
+
+    // Per-thread state kept across the class loop is deliberately small (registers: three CTAs per SM): the packed
+    // gradient scales, the packed sums and a bit mask of the 8-class blocks that contain a positive anchor's class.
+    // The rare blocks / remainder planes that need more re-read the assignments (L1/L2 hits).
+    const int32_t *mp = P.matches + (size_t)b * P.A + g.off[l] + p * K + k;
+    rn_f2 ga2[NPK];
+    unsigned long long posblocks = 0ull;  // bit i: a positive class in [c_chunk0 + 8i, +8)
+    bool anypos = false;
+    const int c_begin = chunk * P.cchunk;
+    const int c_end = min(C, c_begin + P.cchunk);
+    {
+        float ga[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const int m = __ldg(mp + e * K);
+            ga[e] = ((m == RN_MATCH_IGNORE) ? 0.0f : P.a_neg) * gl;  // ignored anchors contribute nothing
+            if (m >= 0) {
+                anypos = true;
+                const int blk = (s_cat[m] - c_begin) / RN_LVL_U;
+                if (s_cat[m] >= c_begin && s_cat[m] < c_end) posblocks |= (blk < 64) ? (1ull << blk) : ~0ull;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < NPK; ++h) ga2[h] = (V >= 2) ? rn_pack(ga[2 * h], ga[(2 * h + 1) % V]) : rn_splat(ga[0]);
+    }
+    if (P.cchunk > 64 * RN_LVL_U && anypos) posblocks = ~0ull;
+    const float ga_pos = P.a_pos * gl;
+
+    const size_t plane0 = ((size_t)b * K + k) * C;  // first class plane of (b, k)
+    const float *xp = P.clas[l] + plane0 * Pl + p;
+    float *dp = GRAD ? P.dclas[l] + plane0 * Pl + p : nullptr;
+    float *pp = (LOGITS && P.probs[l]) ? P.probs[l] + plane0 * Pl + p : nullptr;
+
+    rn_f2 acc2[NPK];
+#pragma unroll
+    for (int h = 0; h < NPK; ++h) acc2[h] = 0ull;
+
+    int c = c_begin;
+#pragma unroll 1
+    for (; c + RN_LVL_U <= c_end; c += RN_LVL_U) {
+        RnLv<V> xv[RN_LVL_U];
+        const float *xq = xp + (size_t)c * Pl;
+#pragma unroll
+        for (int u = 0; u < RN_LVL_U; ++u) xv[u].load(xq + u * Pl);
+        float *dq = GRAD ? dp + (size_t)c * Pl : nullptr;
+        float *pq = (LOGITS && pp) ? pp + (size_t)c * Pl : nullptr;
+        const bool slow = (posblocks >> min((c - c_begin) / RN_LVL_U, 63)) & 1ull;
+        if (!slow && G2) {  // common case: every element has target 0; arithmetic packed two-wide
+            if (V >= 2) {
+#pragma unroll
+                for (int u = 0; u < RN_LVL_U; ++u) {
+                    RnLv<V> gv;
+#pragma unroll
+                    for (int h = 0; h < NPK; ++h) {
+                        float y0 = xv[u].at(2 * h), y1 = xv[u].at((2 * h + 1) % V);
+                        if (LOGITS) rn_sigmoid_pair(y0, y1, y0, y1);
+                        float g0 = 0.f, g1 = 0.f;
+                        rn_focal_pair_neg<GRAD>(y0, y1, P.lo, P.hi, ga2[h], acc2[h], g0, g1);
+                        if (LOGITS && GRAD) {  // sigmoid backward: grad * (1 - y) * y
+                            g0 = (g0 * (1.0f - y0)) * y0;
+                            g1 = (g1 * (1.0f - y1)) * y1;
+                        }
+                        gv.at(2 * h) = g0;
+                        gv.at((2 * h + 1) % V) = g1;
+                        if (LOGITS && pp) {
+                            xv[u].at(2 * h) = y0;
+                            xv[u].at((2 * h + 1) % V) = y1;
+                        }
+                    }
+                    if (LOGITS && pp) xv[u].store(pq + u * Pl);
+                    if (GRAD) gv.store(dq + u * Pl);
+                }
+            } else {  // V == 1: pair two class planes of the same cell
+#pragma unroll
+                for (int u = 0; u < RN_LVL_U; u += 2) {
+                    float y0 = xv[u].at(0), y1 = xv[u + 1].at(0);
+                    if (LOGITS) rn_sigmoid_pair(y0, y1, y0, y1);
+                    float g0 = 0.f, g1 = 0.f;
+                    rn_focal_pair_neg<GRAD>(y0, y1, P.lo, P.hi, ga2[0], acc2[0], g0, g1);
+                    if (LOGITS && GRAD) {
+                        g0 = (g0 * (1.0f - y0)) * y0;
+                        g1 = (g1 * (1.0f - y1)) * y1;
+                    }
+                    if (LOGITS && pp) {
+                        pq[u * Pl] = y0;
+                        pq[(u + 1) * Pl] = y1;
+                    }
+                    if (GRAD) {
+                        RnLv<V> gv;
+                        gv.at(0) = g0;
+                        gv.store(dq + u * Pl);
+                        gv.at(0) = g1;
+                        gv.store(dq + (u + 1) * Pl);
+                    }
+                }
+            }
+        } else {  // a positive anchor's class lies in this block (Vision.py:1588-1593), or gamma != 2
+            int pc[V];
+            float a_row[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const int m = __ldg(mp + e * K);
+                pc[e] = m >= 0 ? s_cat[m] : -1;
+                a_row[e] = (m == RN_MATCH_IGNORE) ? 0.0f : P.a_neg;
+            }
+#pragma unroll
+            for (int u = 0; u < RN_LVL_U; ++u) {
+                RnLv<V> gv;
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    float y = xv[u].at(e);
+                    if (LOGITS) {
+                        float dummy;
+                        rn_sigmoid_pair(y, y, y, dummy);
+                    }
+                    float t = 0.0f;
+                    float gq = rn_focal_elem_rt<G2, GRAD>(pc[e] == c + u, y, P, a_row[e] * gl, ga_pos, t, acc_pos);
+                    acc_neg_w = fmaf(0.5f * a_row[e], t, acc_neg_w);
+                    if (LOGITS && GRAD) gq = (gq * (1.0f - y)) * y;
+                    gv.at(e) = gq;
+                    if (LOGITS && pp) xv[u].at(e) = y;
+                }
+                if (LOGITS && pp) xv[u].store(pq + u * Pl);
+                if (GRAD) gv.store(dq + u * Pl);
+            }
+        }
+    }
+#pragma unroll 1
+    for (; c < c_end; ++c) {  // remainder planes (chunk length not a multiple of RN_LVL_U)
+        RnLv<V> xv, gv;
+        xv.load(xp + (size_t)c * Pl);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const int m = __ldg(mp + e * K);
+            const float a_row = (m == RN_MATCH_IGNORE) ? 0.0f : P.a_neg;
+            float y = xv.at(e);
+            if (LOGITS) {
+                float dummy;
+                rn_sigmoid_pair(y, y, y, dummy);
+            }
+            float t = 0.0f;
+            float gq = rn_focal_elem_rt<G2, GRAD>(m >= 0 && s_cat[m] == c, y, P, a_row * gl, ga_pos, t, acc_pos);
+            acc_neg_w = fmaf(0.5f * a_row, t, acc_neg_w);
+            if (LOGITS && GRAD) gq = (gq * (1.0f - y)) * y;
+            gv.at(e) = gq;
+            if (LOGITS && pp) xv.at(e) = y;
+        }
+        if (LOGITS && pp) xv.store(pp + (size_t)c * Pl);
+        if (GRAD) gv.store(dp + (size_t)c * Pl);
+    }
+    // weight the packed per-cell sums: 0.5 * (1 - alpha) * sum(pw * -2 log q), zero for ignored anchors
+    int m[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) m[e] = __ldg(mp + e * K);
+#pragma unroll
+    for (int h = 0; h < NPK; ++h) {
+        float s0, s1;
+        rn_unpack(acc2[h], s0, s1);
+        if (V >= 2) {
+            acc_neg_w = fmaf(0.5f * ((m[2 * h] == RN_MATCH_IGNORE) ? 0.0f : P.a_neg), s0, acc_neg_w);
+            acc_neg_w = fmaf(0.5f * ((m[(2 * h + 1) % V] == RN_MATCH_IGNORE) ? 0.0f : P.a_neg), s1, acc_neg_w);
+        } else {
+            acc_neg_w = fmaf(0.5f * ((m[0] == RN_MATCH_IGNORE) ? 0.0f : P.a_neg), s0 + s1, acc_neg_w);
+        }
+    }
+
+    // ---- regression rows of this thread: smooth L1 (Vision.py:1532-1566); done by the CTA of class chunk 0 ----
+    if (chunk != 0) return;
+    const size_t rplane0 = ((size_t)b * K + k) * 4;
+    const float *rp = P.reg[l] + rplane0 * Pl + p;
+    RnLv<V> gj[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < V; ++e) gj[j].at(e) = 0.0f;
+    if (anypos) {
+        const float numel = (float)(4 * n_pos);
+        const float ge = n_pos > 0 ? __fdiv_rn(P.wr_over_bs, numel) : 0.0f;  // mean() backward
+        const float knee = (float)(1.0 / 9.0), off = (float)(0.5 / 9.0);       // Vision.py:1565
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            if (m[e] < 0) continue;
+            const float4 an = rn_anchor_from_param(g, nullptr, g.off[l] + (p + e) * K + k);
+            const float4 tg = s_box[m[e]];
+            const float aw = __fsub_rn(an.z, an.x), ah = __fsub_rn(an.w, an.y);
+            const float acx = __fadd_rn(an.x, __fmul_rn(0.5f, aw)), acy = __fadd_rn(an.y, __fmul_rn(0.5f, ah));
+            float tw = __fsub_rn(tg.z, tg.x), th = __fsub_rn(tg.w, tg.y);
+            const float tcx = __fadd_rn(tg.x, __fmul_rn(0.5f, tw)), tcy = __fadd_rn(tg.y, __fmul_rn(0.5f, th));
+            tw = fmaxf(tw, 1.0f);  // Vision.py:1553-1554
+            th = fmaxf(th, 1.0f);
+            float ts[4];
+            ts[0] = __fdiv_rn(__fdiv_rn(__fsub_rn(tcx, acx), aw), 0.1f);  // Vision.py:1556, :1562
+            ts[1] = __fdiv_rn(__fdiv_rn(__fsub_rn(tcy, acy), ah), 0.1f);
+            ts[2] = __fdiv_rn(logf(__fdiv_rn(tw, aw)), 0.2f);             // Vision.py:1558
+            ts[3] = __fdiv_rn(logf(__fdiv_rn(th, ah)), 0.2f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float pv = __ldg(rp + (size_t)j * Pl + e);
+                const float d = __fsub_rn(ts[j], pv);
+                const float diff = fabsf(d);
+                float lj, gd;
+                if (diff < knee) {
+                    lj = __fmul_rn(4.5f, __fmul_rn(diff, diff));
+                    gd = __fmul_rn(__fmul_rn(ge, 4.5f), __fmul_rn(2.0f, diff));
+                } else {
+                    lj = __fsub_rn(diff, off);
+                    gd = ge;
+                }
+                acc_reg += lj;
+                gj[j].at(e) = d > 0.0f ? -gd : (d < 0.0f ? gd : 0.0f);  // -sign(t - p) * gd
+            }
+        }
+    }
+    if (GRAD) {
+        float *drp = P.dreg[l] + rplane0 * Pl + p;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gj[j].store(drp + (size_t)j * Pl);
+    }
+}
+
+// grid = (tiles per image x class chunks, B).  blockIdx.x -> (row tile, class chunk), row tile -> level.
+template <bool G2, bool GRAD, bool LOGITS>
+__global__ void __launch_bounds__(RN_THREADS, 3)
+rn_loss_levels_kernel(const __grid_constant__ RnLvlParams P, const __grid_constant__ RnGeom g) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float4 *s_box = reinterpret_cast<float4 *>(smem);
+    int *s_cat = reinterpret_cast<int *>(s_box + P.M);
+    __shared__ float s_red[2][RN_THREADS / 32];
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int chunk = blockIdx.x % P.nchunks;
+    const int tile = blockIdx.x / P.nchunks;
+    const int l = (tile >= P.tile0[1]) + (tile >= P.tile0[2]) + (tile >= P.tile0[3]) + (tile >= P.tile0[4]);
+    const int row_tile = tile - P.tile0[l];
+
+    if (tid < 32) rn_compact_gt(P.gt_boxes + (size_t)b * P.M, P.gt_cats + (size_t)b * P.M, P.M, s_box, nullptr, s_cat);
+    rn_pdl_wait();  // launched with PDL right behind rn_assign: wait for its matches / npos
+
+    const int n_pos = P.npos[b];
+    const float n_norm = fmaxf((float)n_pos, 1.0f);    // clamp(min=1), Vision.py:1530
+    const float gl = __fdiv_rn(P.wc_over_bs, n_norm);  // upstream of every focal term
+    __syncthreads();                                   // s_cat / s_box visible
+
+    float acc_neg = 0.0f, acc_pos = 0.0f, acc_reg = 0.0f;
+    const int V = P.V[l];
+    if (V == 4) rn_lvl_body<4, G2, GRAD, LOGITS>(P, g, b, l, row_tile, chunk, s_box, s_cat, gl, n_pos, acc_neg, acc_pos, acc_reg);
+    else if (V == 2) rn_lvl_body<2, G2, GRAD, LOGITS>(P, g, b, l, row_tile, chunk, s_box, s_cat, gl, n_pos, acc_neg, acc_pos, acc_reg);
+    else rn_lvl_body<1, G2, GRAD, LOGITS>(P, g, b, l, row_tile, chunk, s_box, s_cat, gl, n_pos, acc_neg, acc_pos, acc_reg);
+
+    rn_pdl_trigger();
+    float c = rn_warp_sum(acc_neg + acc_pos);
+    float r = rn_warp_sum(acc_reg);
+    if ((tid & 31) == 0) {
+        s_red[0][tid >> 5] = c;
+        s_red[1][tid >> 5] = r;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float cs = 0.f, rs = 0.f;
+#pragma unroll
+        for (int w = 0; w < RN_THREADS / 32; ++w) {
+            cs += s_red[0][w];
+            rs += s_red[1][w];
+        }
+        reinterpret_cast<float2 *>(P.partials)[(size_t)b * gridDim.x + blockIdx.x] = make_float2(cs, rs);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+struct RnLvlPlan {
+    int P[RN_NUM_LEVELS], V[RN_NUM_LEVELS], tile0[RN_NUM_LEVELS + 1];
+    int A, cchunk, nchunks, grid_x;
+};
+
+static void rn_lvl_plan(RnLvlPlan *pl, int B, int H, int W, int K, int C) {
+    pl->A = 0;
+    pl->tile0[0] = 0;
+    for (int l = 0; l < RN_NUM_LEVELS; ++l) {
+        const int s = 8 << l;
+        const int gh = (H + s - 1) / s, gw = (W + s - 1) / s;  // retinanet.py:488
+        const int P = gh * gw;
+        pl->P[l] = P;
+        pl->V[l] = (P % 4 == 0) ? 4 : ((P % 2 == 0) ? 2 : 1);
+        pl->A += K * P;
+        const int per_tile = RN_THREADS * pl->V[l];
+        pl->tile0[l + 1] = pl->tile0[l] + (K * P + per_tile - 1) / per_tile;
+    }
+    // classes per CTA: as many as possible (the stride-K gather of the assignments and the prologue are paid once
+    // per CTA) while the grid keeps >= ~8 waves of 148 SMs x 3 resident CTAs; multiples of RN_LVL_U.
+    int cchunk = ((C + RN_LVL_U - 1) / RN_LVL_U) * RN_LVL_U;
+    while (cchunk > RN_LVL_U) {
+        const int nch = (C + cchunk - 1) / cchunk;
+        if ((long long)B * pl->tile0[RN_NUM_LEVELS] * nch >= 8LL * 148 * 3) break;
+        cchunk -= RN_LVL_U;
+    }
+    if (cchunk > C) cchunk = C;
+    pl->cchunk = cchunk;
+    pl->nchunks = (C + cchunk - 1) / cchunk;
+    pl->grid_x = pl->tile0[RN_NUM_LEVELS] * pl->nchunks;
+}
+
+extern "C" size_t rn_loss_levels_workspace_bytes(int B, int H, int W, int K, int C) {
+    if (B <= 0 || H <= 0 || W <= 0 || K <= 0 || C <= 0) return 256;
+    RnLvlPlan pl;
+    rn_lvl_plan(&pl, B, H, W, K, C);
+    // worst case over the chunking heuristic: one chunk per RN_LVL_U classes
+    const size_t max_chunks = (size_t)((C + RN_LVL_U - 1) / RN_LVL_U);
+    const size_t partials = sizeof(float2) * (size_t)B * pl.tile0[RN_NUM_LEVELS] * max_chunks;
+    const size_t per_image = sizeof(float) * 2 * (size_t)B;
+    return ((partials + 255) / 256) * 256 + ((per_image + 255) / 256) * 256;
+}
+
+template <bool LOGITS>
+static void rn_launch_levels(bool g2, bool grad, dim3 grid, size_t smem, cudaStream_t s, const RnLvlParams &P, const RnGeom &g) {
+    if (g2 && grad) rn_launch_pdl(rn_loss_levels_kernel<true, true, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
+    else if (g2) rn_launch_pdl(rn_loss_levels_kernel<true, false, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
+    else if (grad) rn_launch_pdl(rn_loss_levels_kernel<false, true, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
+    else rn_launch_pdl(rn_loss_levels_kernel<false, false, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
+}
+
+extern "C" int rn_loss_levels(const float *const *clas_levels, const float *const *reg_levels, int from_logits,
+                              const float *gt_boxes, const int64_t *gt_cats, const int32_t *matches, const int32_t *npos,
+                              int B, int C, int M, int H, int W, const double *base, int K, double alpha, double gamma,
+                              double beta, int B_global, float *const *dclas_levels, float *const *dreg_levels,
+                              float *const *probs_levels, float *out3, void *workspace, size_t workspace_bytes,
+                              void *stream) {
+    if (B <= 0 || C <= 0 || M < 0 || H <= 0 || W <= 0 || K <= 0 || K > RN_MAX_K)
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_levels: B=%d C=%d M=%d H=%d W=%d K=%d", B, C, M, H, W, K);
+    if (!clas_levels || !reg_levels || !matches || !npos || !out3 || !base || (M > 0 && (!gt_boxes || !gt_cats)))
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_levels: null pointer");
+    if ((dclas_levels == nullptr) != (dreg_levels == nullptr))
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_levels: dclas_levels and dreg_levels must both be given or both be NULL");
+    if (probs_levels && !from_logits) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_levels: probs_levels needs from_logits");
+    if (B_global < B) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_levels: B_global=%d < B=%d", B_global, B);
+    if (((uintptr_t)gt_boxes) & 15) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_levels: gt_boxes must be 16-byte aligned");
+    if (workspace_bytes < rn_loss_levels_workspace_bytes(B, H, W, K, C) || !workspace || (((uintptr_t)workspace) & 255))
+        return rn_set_error(RN_ERR_WORKSPACE, "rn_loss_levels: workspace needs %zu bytes, 256-byte aligned",
+                            rn_loss_levels_workspace_bytes(B, H, W, K, C));
+    RnLvlPlan pl;
+    rn_lvl_plan(&pl, B, H, W, K, C);
+    RnGeom g;
+    int rc = rn_build_geom(&g, H, W, base, K, nullptr, pl.A);
+    if (rc) return rc;
+
+    RnLvlParams P;
+    const bool grad = dclas_levels != nullptr;
+    for (int l = 0; l < RN_NUM_LEVELS; ++l) {
+        P.clas[l] = clas_levels[l];
+        P.reg[l] = reg_levels[l];
+        P.dclas[l] = grad ? dclas_levels[l] : nullptr;
+        P.dreg[l] = grad ? dreg_levels[l] : nullptr;
+        P.probs[l] = probs_levels ? probs_levels[l] : nullptr;
+        if (!P.clas[l] || !P.reg[l] || (grad && (!P.dclas[l] || !P.dreg[l])))
+            return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_levels: null level pointer (level %d)", l);
+        if ((((uintptr_t)P.clas[l]) | ((uintptr_t)P.reg[l]) | ((uintptr_t)P.dclas[l]) | ((uintptr_t)P.dreg[l]) |
+             ((uintptr_t)P.probs[l])) & 15)
+            return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_levels: level tensors must be 16-byte aligned (level %d)", l);
+        P.P[l] = pl.P[l];
+        P.V[l] = pl.V[l];
+        P.tile0[l] = pl.tile0[l];
+    }
+    P.tile0[RN_NUM_LEVELS] = pl.tile0[RN_NUM_LEVELS];
+    P.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); P.gt_cats = gt_cats;
+    P.matches = matches; P.npos = npos;
+    P.B = B; P.A = pl.A; P.C = C; P.M = M; P.K = K;
+    P.cchunk = pl.cchunk; P.nchunks = pl.nchunks;
+    P.a_pos = (float)alpha; P.a_neg = (float)(1.0 - alpha);  // Vision.py:1526
+    P.gamma = (float)gamma;
+    P.lo = (float)1e-4; P.hi = (float)(1.0 - 1e-4);          // Vision.py:1524
+    const float bs = (float)B_global;
+    const float w_reg = (float)(1.0 - beta), w_clas = (float)beta;  // Vision.py:1644
+    P.wc_over_bs = w_clas / bs;
+    P.wr_over_bs = w_reg / bs;
+    unsigned char *wsb = reinterpret_cast<unsigned char *>(workspace);
+    const size_t ws_total = rn_loss_levels_workspace_bytes(B, H, W, K, C);
+    P.partials = reinterpret_cast<float *>(wsb);
+    float *per_image = reinterpret_cast<float *>(wsb + ws_total - ((sizeof(float) * 2 * (size_t)B + 255) / 256) * 256);
+
+    const size_t smem = (size_t)M * (sizeof(float4) + sizeof(int));
+    if (smem > 48 * 1024) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_levels: M=%d too large", M);
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid(pl.grid_x, B);
+    const bool g2 = (gamma == 2.0);
+    if (from_logits) rn_launch_levels<true>(g2, grad, grid, smem, s, P, g);
+    else rn_launch_levels<false>(g2, grad, grid, smem, s, P, g);
+    rc = rn_check_launch("rn_loss_levels");
+    if (rc) return rc;
+    rn_launch_pdl(rn_loss_final_kernel, dim3(1), dim3(1024), 0, s, reinterpret_cast<const float2 *>(P.partials), npos, B,
+                  pl.grid_x, w_reg, w_clas, bs, per_image, out3);
+    return rn_check_launch("rn_loss_levels_final");
+}

@@ -1,0 +1,210 @@
+// rn_loss_math.cuh -- element math of the focal loss (shared by the flat [B,A,C] kernel in rn_loss.cu and the
+// NCHW level-tensor kernel in rn_loss_levels.cu) and the final-reduction kernel both are followed by.
+#pragma once
+#include "rn_common.cuh"
+
+// -2*log(v) for v in [2^-20, 1]; max relative error 1.5e-7 (degree-6 minimax on [sqrt(.5), sqrt(2)),
+// fitted for the relative error of log itself).  Branch free, no special cases.
+__device__ __forceinline__ float rn_neg2log(float v) {
+    const int i = __float_as_int(v);
+    const int t = (i - 0x3f3504f3) & 0xff800000;  // exponent (as a float-field multiple of 2^23)
+    const float f = __int_as_float(i - t) - 1.0f;  // mantissa in [sqrt(.5), sqrt(2)) minus 1
+    const float e23 = (float)t;
+    float p = -2.0f * 8.700362962e-02f;
+    p = fmaf(p, f, -2.0f * -1.426749380e-01f);
+    p = fmaf(p, f, -2.0f * 1.491478973e-01f);
+    p = fmaf(p, f, -2.0f * -1.657758280e-01f);
+    p = fmaf(p, f, -2.0f * 1.996306205e-01f);
+    p = fmaf(p, f, -2.0f * -2.500133718e-01f);
+    p = fmaf(p, f, -2.0f * 3.333391077e-01f);
+    const float z = f * f;
+    const float w0 = fmaf(-2.0f, f, z);  // -2*(f - f^2/2)
+    const float r = fmaf(z * f, p, w0);
+    return fmaf(e23, -2.0f * 0.69314718056f / 8388608.0f, r);
+}
+
+__device__ __forceinline__ float rn_rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// LOGITS variant: the class activations are logits and the head's
+// nn.Sigmoid (reference retinanet.py:258,286) is fused here, y = 1 / (1 + exp(-z)), and the gradient is
+// chained through sigmoid's backward, grad * (1 - y) * y.  This scalar form (accurate expf + IEEE divide,
+// the operations of torch's CUDA sigmoid kernel) serves the C % 4 != 0 path; the vector path uses
+// rn_sigmoid_pair below.
+__device__ __forceinline__ float rn_sigmoid(float z) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-z))); }
+
+// One class element.  POS selects the target (t = 1 for the matched class of a positive anchor).
+// Returns the gradient w.r.t. the probability (already scaled by `ga` = alpha-weight * upstream) and
+// adds the focal term divided by (alpha-weight/2) to `acc`.
+//   t = 0:  l = -(1-a) r^g log(q),  dl/dp = (1-a) ( r^g / q - g r^(g-1) log q ),  r = 1-(1-p), q = 1-p
+//   t = 1:  l = -a q^g log(p),      dl/dp = -a ( q^g / p - g q^(g-1) log p )
+// (r, not p, on purpose: the reference computes (1-pt) with pt = 1-p in fp32, Vision.py:1525-1527.)
+template <bool POS, bool G2, bool GRAD>
+__device__ __forceinline__ float rn_focal_elem(float x, float lo, float hi, float gamma, float ga, float &acc) {
+    const float p = fminf(fmaxf(x, lo), hi);  // Vision.py:1524
+    const float q = 1.0f - p;
+    const float u = POS ? q : (1.0f - q);
+    const float v = POS ? p : q;
+    const float l2 = rn_neg2log(v);  // -2 log v  >= 0
+    float pw, pw1;
+    if (G2) {
+        pw1 = u;
+        pw = u * u;  // pow(x, 2.0) == x*x in torch
+    } else {
+        pw1 = powf(u, gamma - 1.0f);
+        pw = pw1 * u;
+    }
+    acc = fmaf(pw, l2, acc);
+    if (!GRAD) return 0.0f;
+    // pw / v - gamma * pw1 * log v  =  pw * rcp(v) + (gamma/2) * pw1 * l2
+    float g = G2 ? fmaf(pw1, l2, pw * rn_rcp_approx(v)) : fmaf(0.5f * gamma * pw1, l2, pw * rn_rcp_approx(v));
+    g *= POS ? -ga : ga;
+    return (p == x) ? g : 0.0f;  // clamp backward: pass-through iff lo <= x <= hi (inclusive)
+}
+
+// ------------------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): one instruction issues two fp32
+// operations.  The loss kernel is limited by instruction issue, not by the fp32 pipes, so packing the
+// arithmetic of two neighbouring class elements halves the issue slots the polynomial and the
+// focal-term algebra need (profiles/r01_summary.md).  Each half is an ordinary IEEE fp32 operation.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long rn_f2;
+__device__ __forceinline__ rn_f2 rn_pack(float a, float b) {
+    rn_f2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void rn_unpack(rn_f2 v, float &a, float &b) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ rn_f2 rn_fma2(rn_f2 a, rn_f2 b, rn_f2 c) {
+    rn_f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ rn_f2 rn_mul2(rn_f2 a, rn_f2 b) {
+    rn_f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ rn_f2 rn_add2(rn_f2 a, rn_f2 b) {
+    rn_f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ rn_f2 rn_splat(float a) { return rn_pack(a, a); }
+
+// sigmoid of two logits, arithmetic packed two-wide: 2^(z * -log2 e) with the product's rounding error
+// carried in a correction term, MUFU.EX2, 1 + e, MUFU.RCP refined by one Newton step.  Within ~5 ulp of the
+// correctly rounded value (MUFU.EX2 itself is a 2-ulp approximation); ~5 issue slots per element instead of
+// the ~17 of expf + an IEEE divide.
+__device__ __forceinline__ void rn_sigmoid_pair(float z0, float z1, float &y0, float &y1) {
+    const rn_f2 z = rn_pack(z0, z1);
+    const rn_f2 c_hi = rn_splat(-1.4426950216293335f);       // float32(-log2 e)
+    const rn_f2 t_hi = rn_mul2(z, c_hi);
+    rn_f2 t_lo = rn_fma2(z, c_hi, t_hi ^ 0x8000000080000000ull);          // exact residual of the product
+    t_lo = rn_fma2(z, rn_splat(-1.925963033500011e-08f), t_lo);           // + z * (-log2 e - float32(-log2 e))
+    float a0, a1;
+    rn_unpack(t_hi, a0, a1);
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+    const rn_f2 eb = rn_pack(e0, e1);
+    const rn_f2 e = rn_fma2(rn_mul2(eb, rn_splat(0.6931471805599453f)), t_lo, eb);  // 2^(t_hi + t_lo)
+    const rn_f2 one = rn_splat(1.0f);
+    const rn_f2 d = rn_add2(e, one);
+    float d0, d1;
+    rn_unpack(d, d0, d1);
+    const rn_f2 r0 = rn_pack(rn_rcp_approx(d0), rn_rcp_approx(d1));
+    const rn_f2 err = rn_fma2(d ^ 0x8000000080000000ull, r0, one);       // 1 - d * r0
+    rn_unpack(rn_fma2(r0, err, r0), y0, y1);
+}
+
+// Two background (target 0) class elements with gamma == 2: same mathematics as
+// rn_focal_elem<false, true, GRAD>, arithmetic packed two-wide.  acc2 accumulates pw * (-2 log q); ga2 holds the two
+// elements' gradient scales.
+template <bool GRAD>
+__device__ __forceinline__ void rn_focal_pair_neg(float x0, float x1, float lo, float hi, rn_f2 ga2, rn_f2 &acc2,
+                                                  float &g0, float &g1) {
+    const float p0 = fminf(fmaxf(x0, lo), hi), p1 = fminf(fmaxf(x1, lo), hi);  // Vision.py:1524
+    const rn_f2 one = rn_splat(1.0f), mone = rn_splat(-1.0f);
+    const rn_f2 q = rn_fma2(rn_pack(p0, p1), mone, one);  // 1 - p  (exact product, one rounding)
+    const rn_f2 u = rn_fma2(q, mone, one);                // 1 - (1 - p), Vision.py:1525-1527
+    float q0, q1;
+    rn_unpack(q, q0, q1);
+    // -2 log(q): range reduction per element (integer), polynomial packed
+    const int i0 = __float_as_int(q0), i1 = __float_as_int(q1);
+    const int t0 = (i0 - 0x3f3504f3) & 0xff800000, t1 = (i1 - 0x3f3504f3) & 0xff800000;
+    const rn_f2 f = rn_add2(rn_pack(__int_as_float(i0 - t0), __int_as_float(i1 - t1)), mone);
+    const rn_f2 e23 = rn_pack((float)t0, (float)t1);
+    rn_f2 p = rn_splat(-2.0f * 8.700362962e-02f);
+    p = rn_fma2(p, f, rn_splat(-2.0f * -1.426749380e-01f));
+    p = rn_fma2(p, f, rn_splat(-2.0f * 1.491478973e-01f));
+    p = rn_fma2(p, f, rn_splat(-2.0f * -1.657758280e-01f));
+    p = rn_fma2(p, f, rn_splat(-2.0f * 1.996306205e-01f));
+    p = rn_fma2(p, f, rn_splat(-2.0f * -2.500133718e-01f));
+    p = rn_fma2(p, f, rn_splat(-2.0f * 3.333391077e-01f));
+    const rn_f2 z = rn_mul2(f, f);
+    const rn_f2 w0 = rn_fma2(rn_splat(-2.0f), f, z);
+    const rn_f2 r = rn_fma2(rn_mul2(z, f), p, w0);
+    const rn_f2 l2 = rn_fma2(e23, rn_splat(-2.0f * 0.69314718056f / 8388608.0f), r);
+    const rn_f2 pw = rn_mul2(u, u);  // pow(x, 2.0) == x*x in torch
+    acc2 = rn_fma2(pw, l2, acc2);
+    if (!GRAD) return;
+    // dl/dp / (alpha weight) = pw / q - 2 u log q = pw * rcp(q) + u * l2
+    rn_f2 g = rn_fma2(u, l2, rn_mul2(pw, rn_pack(rn_rcp_approx(q0), rn_rcp_approx(q1))));
+    g = rn_mul2(g, ga2);
+    rn_unpack(g, g0, g1);
+    g0 = (p0 == x0) ? g0 : 0.0f;  // clamp backward: pass-through iff lo <= x <= hi (inclusive)
+    g1 = (p1 == x1) ? g1 : 0.0f;
+}
+
+// One CTA, one warp per image: sums the image's CTA partials in a fixed order (float64), normalises like
+// the reference (Vision.py:1530, :1566); thread 0 then accumulates over images in fp32 in image order
+// (Vision.py:1640-1641) and combines (Vision.py:1643-1644).  (Folding this into the loss kernel
+// with a last-CTA election -- __threadfence + ticket atomic per CTA -- was measured slower twice, also when
+// only warp 0 stays for the election: COCO step 0.378 -> 0.393 ms, Pascal 78 -> 87 us; profiles/r01_summary.md.)
+static __global__ void __launch_bounds__(1024)
+rn_loss_final_kernel(const float2 *__restrict__ partials, const int32_t *__restrict__ npos, int B, int tiles,
+                     float w_reg, float w_clas, float bs, float *__restrict__ per_image /*[B][2]*/,
+                     float *__restrict__ out3) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    rn_pdl_wait();  // launched with PDL behind the loss kernel: its partials must be complete and visible
+    for (int b = warp; b < B; b += nwarps) {
+        double cs = 0.0, rs = 0.0;
+        const float2 *p = partials + (size_t)b * tiles;
+#pragma unroll 4
+        for (int t = lane; t < tiles; t += 32) {
+            const float2 v = p[t];
+            cs += (double)v.x;
+            rs += (double)v.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cs += __shfl_xor_sync(RN_FULL_MASK, cs, o);
+            rs += __shfl_xor_sync(RN_FULL_MASK, rs, o);
+        }
+        if (lane == 0) {
+            const int n = npos[b];
+            const float n_norm = fmaxf((float)n, 1.0f);
+            per_image[2 * b + 0] = n > 0 ? __fdiv_rn((float)rs, (float)(4 * n)) : 0.0f;  // reg loss of image b
+            per_image[2 * b + 1] = __fdiv_rn((float)cs, n_norm);                          // clas loss of image b
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float reg_total = 0.f, clas_total = 0.f;
+        for (int b = 0; b < B; ++b) {
+            reg_total = __fadd_rn(reg_total, per_image[2 * b + 0]);
+            clas_total = __fadd_rn(clas_total, per_image[2 * b + 1]);
+        }
+        const float reg_loss = __fdiv_rn(reg_total, bs), clas_loss = __fdiv_rn(clas_total, bs);
+        out3[0] = __fadd_rn(__fmul_rn(w_reg, reg_loss), __fmul_rn(w_clas, clas_loss));
+        out3[1] = reg_loss;
+        out3[2] = clas_loss;
+    }
+}
+

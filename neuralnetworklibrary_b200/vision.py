@@ -134,6 +134,96 @@ class _SSDLossFunction(torch.autograd.Function):
         return dreg, dclas, None, None, None, None
 
 
+def level_shapes(H, W, K, n):
+    """Shapes [(K*n, gh_l, gw_l)] of the five NCHW head outputs for an H x W image (retinanet.py:488)."""
+    return [(K * n, -(-H // (8 << l)), -(-W // (8 << l))) for l in range(_lib.NUM_LEVELS)]
+
+
+def _launch_loss_levels(anchors, reg_levels, clas_levels, gt_boxes, gt_cats, cfg, need_grad):
+    """rn_assign + rn_loss_levels on the current stream: the loss on the heads' NCHW level tensors (no permute /
+    view / cat pass, retinanet.py:215-217, :289-295, Vision.py:1467-1468).  Returns (out3, dreg_levels,
+    dclas_levels, matches, npos)."""
+    lib = _lib.load()
+    H, W, base, K, table, A = anchor_args(anchors)
+    if table is not None:
+        raise ValueError("the level-tensor loss needs anchors from this package's AnchorGenerator (geometry tag)")
+    B, M = int(gt_cats.shape[0]), int(gt_cats.shape[1])
+    if len(reg_levels) != _lib.NUM_LEVELS or len(clas_levels) != _lib.NUM_LEVELS:
+        raise ValueError("expected %d level tensors (P3..P7)" % _lib.NUM_LEVELS)
+    if int(clas_levels[0].shape[1]) % K:
+        raise ValueError("class head channels must be a multiple of the %d anchors per cell" % K)
+    Cn = int(clas_levels[0].shape[1]) // K
+    for t, shp in zip(list(clas_levels) + list(reg_levels), level_shapes(H, W, K, Cn) + level_shapes(H, W, K, 4)):
+        _lib.require_cuda(t, "level tensor", torch.float32)
+        if tuple(t.shape) != (B,) + shp or not t.is_contiguous():
+            raise ValueError("level tensor must be contiguous NCHW of shape %s, got %s" % ((B,) + shp, tuple(t.shape)))
+    dev = clas_levels[0].device
+    B_global = cfg["global_batch"] if cfg["global_batch"] else B * cfg["world_size"]
+    matches = torch.empty((B, A), dtype=torch.int32, device=dev)
+    npos = torch.empty((B,), dtype=torch.int32, device=dev)
+    dclas = dreg = probs = None
+    if need_grad:
+        dclas = [torch.empty_like(t) for t in clas_levels]
+        dreg = [torch.empty_like(t) for t in reg_levels]
+    if cfg.get("from_logits") and cfg.get("want_probs"):
+        probs = [torch.empty_like(t) for t in clas_levels]
+    cfg["last_probs"] = probs
+    out3 = torch.empty(3, dtype=torch.float32, device=dev)
+    ws = _ws.get(lib.rn_loss_levels_workspace_bytes(B, H, W, K, Cn), dev)
+    stream = _lib.stream_ptr(dev)
+    _lib.check(lib.rn_assign(_lib.ptr(gt_boxes), _lib.ptr(gt_cats), B, M, H, W, base, K, None, A,
+                             float(cfg["pos_thresh"]), float(cfg["neg_thresh"]), _lib.ptr(matches), _lib.ptr(npos),
+                             None, stream))
+    _lib.check(lib.rn_loss_levels(_lib.ptr_array(clas_levels), _lib.ptr_array(reg_levels), int(bool(cfg.get("from_logits"))),
+                                  _lib.ptr(gt_boxes), _lib.ptr(gt_cats), _lib.ptr(matches), _lib.ptr(npos), B, Cn, M, H, W,
+                                  base, K, float(cfg["alpha"]), float(cfg["gamma"]), float(cfg["beta"]), int(B_global),
+                                  _lib.ptr_array(dclas), _lib.ptr_array(dreg), _lib.ptr_array(probs), _lib.ptr(out3),
+                                  _lib.ptr(ws), ws.numel(), stream))
+    return out3, dreg, dclas, matches, npos
+
+
+class _SSDLossLevelsFunction(torch.autograd.Function):
+    """_SSDLossFunction for per-level NCHW head outputs: inputs are (anchors, gt_boxes, gt_cats, cfg, reg P3..P7,
+    clas P3..P7); backward returns one gradient per level tensor, in the layout of its input."""
+
+    @staticmethod
+    def forward(ctx, anchors, gt_boxes, gt_cats, cfg, *levels):
+        n = _lib.NUM_LEVELS
+        reg_levels, clas_levels = levels[:n], levels[n:]
+        need_grad = any(ctx.needs_input_grad[4:])
+        with torch.cuda.device(clas_levels[0].device):
+            out3, dreg, dclas, matches, npos = _launch_loss_levels(anchors, reg_levels, clas_levels, gt_boxes, gt_cats,
+                                                                  cfg, need_grad)
+        if cfg["world_size"] > 1:
+            out3 = reduce_loss_scalars(out3, cfg["group"])
+        ctx.grads = (dreg, dclas)
+        ctx.used = False
+        cfg["last_matches"], cfg["last_npos"] = matches, npos
+        loss, reg_loss, clas_loss = out3.unbind(0)
+        ctx.mark_non_differentiable(reg_loss, clas_loss)
+        return loss, reg_loss, clas_loss
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_reg, _g_clas):
+        dreg, dclas = ctx.grads
+        n = _lib.NUM_LEVELS
+        if dreg is None:
+            return (None,) * (4 + 2 * n)
+        if ctx.used:
+            raise RuntimeError("SSD_loss: backward through the same loss value twice is not supported; "
+                               "the gradients were produced (and scaled in place) by the first backward")
+        ctx.used = True
+        ctx.grads = None
+        lib = _lib.load()
+        g = g_loss.detach().to(dtype=torch.float32).contiguous()
+        dev = dclas[0].device
+        with torch.cuda.device(dev):
+            for dc, dr in zip(dclas, dreg):
+                _lib.check(lib.rn_scale_grads(_lib.ptr(dc), dc.numel(), _lib.ptr(dr), dr.numel(), _lib.ptr(g),
+                                              _lib.stream_ptr(dev)))
+        return (None, None, None, None) + tuple(dreg) + tuple(dclas)
+
+
 class CapturedLossStep(object):
     """SSD_loss forward+backward for fixed shapes, captured once into a CUDA graph and replayed with a
     single launch (assignment kernel + fused loss/gradient/reduction kernel).  For launch-bound loops: the
@@ -210,6 +300,8 @@ class SSD_loss(object):
 
     def __call__(self, activ, target):
         anchors, reg, clas = activ[0], activ[1], activ[2]
+        if isinstance(clas, (list, tuple)):
+            return self._call_levels(anchors, reg, clas, target)
         _lib.require_cuda(reg, "reg", torch.float32)
         _lib.require_cuda(clas, "clas", torch.float32)
         gt_boxes, gt_cats = _targets(target, clas.device)
@@ -225,6 +317,27 @@ class SSD_loss(object):
                    global_batch=self.global_batch, from_logits=self.from_logits, want_probs=self.keep_probs)
         loss, reg_loss, clas_loss = _SSDLossFunction.apply(reg.contiguous(), clas.contiguous(), anchors, gt_boxes,
                                                            gt_cats, cfg)
+        self._cfg = cfg
+        self.reg_loss, self.clas_loss = reg_loss, clas_loss   # Vision.py:1643
+        return loss
+
+    def _cfg_for_call(self):
+        world = 1
+        if self.distributed:
+            import torch.distributed as dist
+            world = dist.get_world_size(self.process_group)
+        return dict(alpha=self.alpha, gamma=self.gamma, beta=self.beta, pos_thresh=self.pos_thresh,
+                    neg_thresh=self.neg_thresh, world_size=world, group=self.process_group,
+                    global_batch=self.global_batch, from_logits=self.from_logits, want_probs=self.keep_probs)
+
+    def _call_levels(self, anchors, reg_levels, clas_levels, target):
+        """activ = [anchors, [reg P3..P7], [clas P3..P7]] with the heads' NCHW conv outputs (reg_l [bs, 9*4, gh, gw],
+        clas_l [bs, 9*C, gh, gw]) instead of the permuted + concatenated [bs, A, 4|C] tensors: same loss and metrics,
+        gradients arrive in the level tensors' own layout (needs an
+        ObjectDetectionNet.forward that skips retinanet.py:215-217, :289-295 and Vision.py:1467-1468)."""
+        gt_boxes, gt_cats = _targets(target, clas_levels[0].device)
+        cfg = self._cfg_for_call()
+        loss, reg_loss, clas_loss = _SSDLossLevelsFunction.apply(anchors, gt_boxes, gt_cats, cfg, *reg_levels, *clas_levels)
         self._cfg = cfg
         self.reg_loss, self.clas_loss = reg_loss, clas_loss   # Vision.py:1643
         return loss

@@ -259,3 +259,24 @@ def map_table(predictions, targets, C, thresholds):
             with np.errstate(divide="ignore", invalid="ignore"):
                 table[t, c] = np.sum(prec_max[ic_sorted.nonzero()[0]]) / np.float64(ntrue)       # Vision.py:1741-1747
     return table
+
+
+def heads_to_flat(levels, n):
+    """The tail of the reference's heads + the model's concatenation in numpy: each level [B, K*n, gh, gw] ->
+    permute(0,2,3,1).contiguous().view(B, -1, n) (retinanet.py:215-217, :289-295), levels concatenated on axis 1
+    (Vision.py:1467-1468).  Returns [B, A, n]."""
+    return np.concatenate([np.ascontiguousarray(np.transpose(x, (0, 2, 3, 1))).reshape(x.shape[0], -1, n) for x in levels],
+                          axis=1)
+
+
+def flat_to_heads(flat, level_shapes):
+    """Inverse of heads_to_flat (what autograd does to a gradient w.r.t. the flat tensor): [B, A, n] -> list of
+    [B, K*n, gh, gw]; level_shapes = [(K*n, gh, gw)]."""
+    B, _, n = flat.shape
+    out, a0 = [], 0
+    for (ch, gh, gw) in level_shapes:
+        rows = gh * gw * (ch // n)
+        out.append(np.ascontiguousarray(np.transpose(flat[:, a0:a0 + rows].reshape(B, gh, gw, ch), (0, 3, 1, 2))))
+        a0 += rows
+    assert a0 == flat.shape[1]
+    return out

@@ -1,0 +1,119 @@
+"""GPU parity of the level-tensor loss (rn_loss_levels): SSD_loss called with the heads'
+NCHW conv outputs per pyramid level instead of the permuted + concatenated [bs, A, 4|C] tensors.  The checker is the
+CPU oracle on the flat tensors, with the layout map of retinanet.py:215-217, :289-295 / Vision.py:1467-1468 restated
+in oracle.heads_to_flat (pinned against the unmodified reference heads in tests/test_oracle_vs_reference.py).
+Assignments bit-exact; loss and gradients rtol 1e-5 with identical zero patterns (dreg: the scaled tolerance of
+neuralnetworklibrary_b200/testing.py)."""
+import numpy as np
+import pytest
+import torch
+
+from neuralnetworklibrary_b200 import testing as syn
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _setup(seed, H, W, C, B, M, logits=False):
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator
+    from neuralnetworklibrary_b200.vision import level_shapes
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=dev()))
+    an = orc.anchors(H, W)
+    gb, gc = syn.make_targets(B, M, H, W, C, seed=seed, min_side=10.0, max_frac=0.7)
+    g = torch.Generator().manual_seed(seed)
+    if logits:
+        flat_c = torch.randn(B, an.shape[0], C, generator=g) * 1.5 - 4.6
+        flat_c.view(-1)[:64] = torch.linspace(-12, 12, 64)
+        flat_r = torch.randn(B, an.shape[0], 4, generator=g) * 0.5
+    else:
+        flat_c, flat_r = syn.make_train_activations(B, an.shape[0], C, seed=seed, edge_cases=64)
+    cs, rs = level_shapes(H, W, 9, C), level_shapes(H, W, 9, 4)
+    clas_lv = [torch.from_numpy(x) for x in orc.flat_to_heads(flat_c.numpy(), cs)]
+    reg_lv = [torch.from_numpy(x) for x in orc.flat_to_heads(flat_r.numpy(), rs)]
+    assert np.array_equal(orc.heads_to_flat([t.numpy() for t in clas_lv], C), flat_c.numpy())
+    return anchors, an, gb, gc, flat_c, flat_r, clas_lv, reg_lv, cs, rs
+
+
+# shapes: all levels V=4 (128x128: P = 256 .. 1); mixed V (100x167: 2171 odd, 546 even ...; 800x1344-like 200x336)
+@pytest.mark.parametrize("seed,H,W,C,B,M,kw", [
+    (301, 128, 128, 20, 2, 6, {}),
+    (302, 100, 167, 80, 2, 5, {}),
+    (303, 200, 336, 80, 2, 8, dict(beta=0.3, alpha=0.4)),
+    (304, 96, 160, 7, 3, 4, {}),
+    (305, 64, 96, 12, 2, 4, dict(gamma=1.5)),
+    (306, 256, 256, 91, 1, 10, {}),
+])
+def test_levels_loss_matches_oracle(seed, H, W, C, B, M, kw):
+    from neuralnetworklibrary_b200.vision import SSD_loss
+    anchors, an, gb, gc, flat_c, flat_r, clas_lv, reg_lv, cs, rs = _setup(seed, H, W, C, B, M)
+    cd = [t.to(dev()).requires_grad_(True) for t in clas_lv]
+    rd = [t.to(dev()).requires_grad_(True) for t in reg_lv]
+    f = SSD_loss(**kw)
+    loss = f([anchors, rd, cd], [gb.to(dev()), gc.to(dev())])
+    loss.backward()
+    o = orc.loss(an, flat_c.numpy(), flat_r.numpy(), gb.numpy(), gc.numpy(), want_matches=True, **kw)
+    matches, npos = f.last_assignment
+    assert np.array_equal(matches.cpu().numpy(), o["matches"])
+    got3 = np.array([loss.item(), f.reg_loss.item(), f.clas_loss.item()], np.float32)
+    np.testing.assert_allclose(got3, o["out3"], rtol=RTOL, atol=0)
+    syn.assert_rel(orc.heads_to_flat([t.grad.cpu().numpy() for t in cd], C), o["dclas"], what="dclas")
+    syn.assert_dreg_close(orc.heads_to_flat([t.grad.cpu().numpy() for t in rd], 4), o["dreg"])
+    # the flat path of this library on the permuted tensors: same assignment, loss within rtol
+    with torch.no_grad():
+        l_flat = SSD_loss(**kw)([anchors, flat_r.to(dev()), flat_c.to(dev())], [gb.to(dev()), gc.to(dev())])
+    np.testing.assert_allclose(l_flat.item(), loss.item(), rtol=RTOL)
+
+
+@pytest.mark.parametrize("seed,H,W,C,B,M", [(311, 128, 160, 80, 2, 6), (312, 100, 167, 20, 2, 5), (313, 96, 96, 7, 2, 4)])
+def test_levels_loss_from_logits(seed, H, W, C, B, M):
+    """Sigmoid fused (as rn_loss_logits): the oracle is fed the kernel's own probabilities, see
+    tests/test_gpu_assign_loss.py::test_loss_from_logits for why."""
+    from neuralnetworklibrary_b200.vision import SSD_loss
+    anchors, an, gb, gc, flat_z, flat_r, z_lv, reg_lv, cs, rs = _setup(seed, H, W, C, B, M, logits=True)
+    zd = [t.to(dev()).requires_grad_(True) for t in z_lv]
+    rd = [t.to(dev()).requires_grad_(True) for t in reg_lv]
+    f = SSD_loss(from_logits=True, keep_probs=True)
+    loss = f([anchors, rd, zd], [gb.to(dev()), gc.to(dev())])
+    loss.backward()
+    y = orc.heads_to_flat([t.cpu().numpy() for t in f.last_probs], C)
+    exact = 1.0 / (1.0 + np.exp(-flat_z.numpy().astype(np.float64)))
+    ulp = np.abs(y.view(np.int32).astype(np.int64) - exact.astype(np.float32).view(np.int32).astype(np.int64))
+    assert ulp.max() <= 6
+    o = orc.loss(an, y, flat_r.numpy(), gb.numpy(), gc.numpy(), want_matches=True)
+    got3 = np.array([loss.item(), f.reg_loss.item(), f.clas_loss.item()], np.float32)
+    np.testing.assert_allclose(got3, o["out3"], rtol=RTOL, atol=0)
+    syn.assert_rel(orc.heads_to_flat([t.grad.cpu().numpy() for t in zd], C), (o["dclas"] * (np.float32(1) - y)) * y, what="dlogits")
+    syn.assert_dreg_close(orc.heads_to_flat([t.grad.cpu().numpy() for t in rd], 4), o["dreg"])
+
+
+def test_levels_no_grad_and_upstream_scale():
+    from neuralnetworklibrary_b200.vision import SSD_loss
+    anchors, an, gb, gc, flat_c, flat_r, clas_lv, reg_lv, cs, rs = _setup(321, 96, 128, 20, 2, 5)
+    tgt = [gb.to(dev()), gc.to(dev())]
+    f = SSD_loss()
+    with torch.no_grad():
+        l0 = f([anchors, [t.to(dev()) for t in reg_lv], [t.to(dev()) for t in clas_lv]], tgt)
+    cd = [t.to(dev()).requires_grad_(True) for t in clas_lv]
+    rd = [t.to(dev()).requires_grad_(True) for t in reg_lv]
+    l1 = f([anchors, rd, cd], tgt)
+    assert l0.item() == l1.item()
+    (l1 * 3.0).backward()
+    o = orc.loss(an, flat_c.numpy(), flat_r.numpy(), gb.numpy(), gc.numpy())
+    syn.assert_rel(orc.heads_to_flat([t.grad.cpu().numpy() for t in cd], 20), o["dclas"] * np.float32(3), what="dclas*3")
+
+
+def test_levels_rejects_wrong_shapes():
+    from neuralnetworklibrary_b200.vision import SSD_loss
+    anchors, an, gb, gc, flat_c, flat_r, clas_lv, reg_lv, cs, rs = _setup(322, 64, 64, 4, 1, 2)
+    tgt = [gb.to(dev()), gc.to(dev())]
+    bad = [t.to(dev()) for t in clas_lv]
+    bad[2] = bad[2][:, :, :-1].contiguous()
+    with pytest.raises(ValueError):
+        SSD_loss()([anchors, [t.to(dev()) for t in reg_lv], bad], tgt)
+    with pytest.raises(ValueError):
+        SSD_loss()([anchors.clone(), [t.to(dev()) for t in reg_lv], [t.to(dev()) for t in clas_lv]], tgt)

@@ -77,3 +77,38 @@ def test_loss_from_logits(seed, H, W, C, B, M):
     assert_rel(np.where(same, o2["dclas"], 0), np.where(same, r["dclas"], 0))
     ulp = np.abs(y2.view(np.int32).astype(np.int64) - y.view(np.int32).astype(np.int64))
     assert ulp.max() <= 2
+
+
+@pytest.mark.parametrize("H,W,C", [(64, 96, 3), (100, 167, 5)])
+def test_heads_layout_restatement(H, W, C):
+    """oracle.heads_to_flat / flat_to_heads against the UNMODIFIED heads of the reference (retinanet.py:215-217,
+    :289-295) and the model's concatenation (Vision.py:1467-1468): the conv outputs are captured with forward
+    hooks, and autograd's gradient w.r.t. them is the inverse layout map."""
+    import torch
+    from oracle import ref_shim
+    rn, _ = ref_shim.load()
+    torch.manual_seed(3)
+    K, F, B = 9, 4, 2
+    cls_head = rn.ClassificationModel(F, num_anchors=K, num_classes=C, feature_size=F)
+    reg_head = rn.RegressionModel(F, num_anchors=K, feature_size=F)
+    grabbed = {"c": [], "r": []}
+
+    def grab(key):
+        def hook(module, inputs, output):
+            output.retain_grad()
+            grabbed[key].append(output)
+        return hook
+
+    cls_head.output_act.register_forward_hook(grab("c"))
+    reg_head.output.register_forward_hook(grab("r"))
+    feats = [torch.randn(B, F, -(-H // (8 << l)), -(-W // (8 << l))) for l in range(5)]
+    clas = torch.cat([cls_head(f) for f in feats], dim=1)
+    reg = torch.cat([reg_head(f) for f in feats], dim=1)
+    assert np.array_equal(orc.heads_to_flat([t.detach().numpy() for t in grabbed["c"]], C), clas.detach().numpy())
+    assert np.array_equal(orc.heads_to_flat([t.detach().numpy() for t in grabbed["r"]], 4), reg.detach().numpy())
+    wc, wr = torch.randn_like(clas), torch.randn_like(reg)
+    ((clas * wc).sum() + (reg * wr).sum()).backward()
+    for got, t in zip(orc.flat_to_heads(wc.numpy(), [tuple(t.shape[1:]) for t in grabbed["c"]]), grabbed["c"]):
+        assert np.array_equal(got, t.grad.numpy())
+    for got, t in zip(orc.flat_to_heads(wr.numpy(), [tuple(t.shape[1:]) for t in grabbed["r"]]), grabbed["r"]):
+        assert np.array_equal(got, t.grad.numpy())
