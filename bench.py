@@ -206,6 +206,62 @@ def time_loss_graph(anchors, sets, steps, warmup, device, world, from_logits=Fal
     return total_ms, launches, float(out3[0].item())
 
 
+def time_loss_levels(cfg, B, steps, warmup, device, from_logits):
+    """The loss step on the heads' NCHW level tensors (rn_assign + rn_loss_levels + final reduction) as CUDA-graph
+    replays; 2 rotating input sets (each larger than L2)."""
+    import torch
+
+    from neuralnetworklibrary_b200 import testing as syn
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator
+    from neuralnetworklibrary_b200.vision import _launch_loss_levels, level_shapes
+
+    H, W, C, M = cfg["H"], cfg["W"], cfg["C"], cfg["M"]
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=device))
+    g = torch.Generator(device=device).manual_seed(1007)
+    sets = []
+    for k in range(2):
+        clas = []
+        for shp in level_shapes(H, W, 9, C):
+            z = torch.randn((B,) + shp, generator=g, device=device) - 4.6
+            clas.append(z if from_logits else torch.sigmoid_(z))
+        reg = [torch.randn((B,) + shp, generator=g, device=device) * 0.5 for shp in level_shapes(H, W, 9, 4)]
+        gb, gc = syn.make_targets(B, M, H, W, C, seed=1007 + k)
+        sets.append((reg, clas, gb.to(device), gc.to(device)))
+    run_cfg = dict(alpha=0.25, gamma=2.0, beta=0.5, pos_thresh=0.5, neg_thresh=0.4, world_size=1, group=None,
+                   global_batch=B, from_logits=from_logits)
+
+    # one CUDA graph per input set (assign + level loss + final reduction; outputs live in the graph's pool)
+    graphs, outs = [], []
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        for reg, clas, gb, gc in sets:
+            _launch_loss_levels(anchors, reg, clas, gb, gc, run_cfg, True)
+    torch.cuda.current_stream(device).wait_stream(side)
+    torch.cuda.synchronize(device)
+    for reg, clas, gb, gc in sets:
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            res = _launch_loss_levels(anchors, reg, clas, gb, gc, run_cfg, True)
+        graphs.append(gr)
+        outs.append(res)
+
+    def step(k):
+        graphs[k % 2].replay()
+        return outs[k % 2][0]
+
+    for k in range(warmup):
+        step(k)
+    torch.cuda.synchronize(device)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for k in range(steps):
+        out3 = step(warmup + k)
+    t1.record()
+    torch.cuda.synchronize(device)
+    return t0.elapsed_time(t1), float(out3[0].item())
+
+
 def time_loss_eager(anchors, sets, steps, warmup, device):
     """The same step through SSD_loss(...) + loss.backward() call by call, with CUDA events around the
     rn_loss library call (the dominant streaming kernel + its small final reduction)."""
@@ -458,6 +514,17 @@ def run_ours(args):
                                       "backward (not counted here)"}
         except Exception as exc:
             line["logits"] = {"error": repr(exc)}
+        for key, fl in (("levels", False), ("levels_logits", True)):
+            try:  # SURVEY.md section 8f row 1, second half: the loss on the heads' NCHW level tensors
+                vt, _ = time_loss_levels(COCO, B, args.steps, args.warmup, device, fl)
+                line[key] = {"workload": "coco_loss_fwd_bwd on the heads' NCHW level tensors%s, B=%d 800x1344 C=80"
+                                         % (" (logits, sigmoid fused)" if fl else "", B),
+                             "images_per_s": round(B * args.steps / (vt * 1e-3), 1), "ms_per_step": round(vt / args.steps, 4),
+                             "roofline_frac_whole_step": round(loss_bytes(B, A, COCO["C"]) * args.steps / (vt * 1e-3) / 1e9 / peak, 4),
+                             "note": "removes the permute/contiguous/view and cat passes over [B,A,C] from the model's "
+                                     "forward and backward (not counted here)"}
+            except Exception as exc:
+                line[key] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_baseline_loss(COCO)
             line["cpu_baseline"] = {"value": round(v, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}

@@ -14,9 +14,36 @@
 // independent V*4-byte loads in flight, exactly the element math of rn_loss.cu, V*4-byte streaming stores for the
 // gradient.  A warp therefore reads/writes 32*V*4 contiguous bytes per plane.  Algorithmic bytes are unchanged:
 // 8*A*(C+4) per image with gradients.  No tensor cores: there is no contraction on this path.
+#include <stdlib.h>
+
 #include "rn_loss_math.cuh"
 
-#define RN_LVL_U 8  // class planes in flight per thread
+// Tuning (measured on B200, COCO B=16, A/B runs inside one gpurun call next to the flat kernel; profiles/r01_summary.md):
+// the probability variant is latency bound -- 8 planes in flight per thread, 128-thread CTAs at 6 per SM (80 registers;
+// 4 planes in flight: 0.51 ms instead of 0.42; double buffering at 2 CTAs/SM: no gain) -- and the logits variant issue
+// bound (the fused sigmoid adds ~10 instructions per element): 4 planes, 256-thread CTAs at 4 per SM (64 registers,
+// 0.496 ms; with the probability variant's shape 0.54 ms).  More class chunks per row tile are slower (the CTA
+// prologue -- ground-truth compaction, barrier, stride-K gather -- is paid per chunk): 1 chunk 0.416, 5 chunks 0.463 ms.
+#define RN_LVL_CHUNK_Q 8  // class chunks are multiples of this
+#ifndef RN_LVL_THREADS_PROB
+#define RN_LVL_THREADS_PROB 128
+#endif
+#ifndef RN_LVL_THREADS_LOGIT
+#define RN_LVL_THREADS_LOGIT 256
+#endif
+#define RN_LVL_THREADS_MAX 256
+#ifndef RN_LVL_U_PROB
+#define RN_LVL_U_PROB 8
+#endif
+#ifndef RN_LVL_CTAS_PROB
+#define RN_LVL_CTAS_PROB 6
+#endif
+#ifndef RN_LVL_U_LOGIT
+#define RN_LVL_U_LOGIT 4
+#endif
+#ifndef RN_LVL_CTAS_LOGIT
+#define RN_LVL_CTAS_LOGIT 4
+#endif
 
 struct RnLvlParams {
     const float *clas[RN_NUM_LEVELS];
@@ -84,180 +111,194 @@ __device__ __forceinline__ float rn_focal_elem_rt(bool pos, float x, const RnLvl
 }
 
 // The work of one thread: V cells of one (image, level, slot), classes [c_begin, c_end).
-template <int V, bool G2, bool GRAD, bool LOGITS>
+template <int V, int U, bool G2, bool GRAD, bool LOGITS>
 __device__ __forceinline__ void rn_lvl_body(const RnLvlParams &P, const RnGeom &g, int b, int l, int row_tile, int chunk,
-                                            const float4 *s_box, const int *s_cat, float gl, int n_pos, float &acc_neg_w,
-                                            float &acc_pos, float &acc_reg) {
+                                            float4 *s_box, int *s_cat, float &acc_neg_w, float &acc_pos, float &acc_reg) {
     constexpr int NPK = (V >= 2) ? V / 2 : 1;  // packed accumulators
     const int Pl = P.P[l], K = P.K, C = P.C;
     const int rows = K * Pl;
-    const int r0 = (row_tile * RN_THREADS + threadIdx.x) * V;
-    if (r0 >= rows) return;
-    const int k = r0 / Pl;
-    const int p = r0 - k * Pl;
-
-    // Per-thread state kept across the class loop is deliberately small (registers: three CTAs per SM): the packed
-    // gradient scales, the packed sums and a bit mask of the 8-class blocks that contain a positive anchor's class.
-    // The rare blocks / remainder planes that need more re-read the assignments (L1/L2 hits).
-    const int32_t *mp = P.matches + (size_t)b * P.A + g.off[l] + p * K + k;
-    rn_f2 ga2[NPK];
-    unsigned long long posblocks = 0ull;  // bit i: a positive class in [c_chunk0 + 8i, +8)
-    bool anypos = false;
+    const int r0 = (row_tile * (int)blockDim.x + threadIdx.x) * V;
+    const bool valid = r0 < rows;
+    const int k = valid ? r0 / Pl : 0;
+    const int p = valid ? r0 - k * Pl : 0;
     const int c_begin = chunk * P.cchunk;
     const int c_end = min(C, c_begin + P.cchunk);
-    {
-        float ga[V];
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-            const int m = __ldg(mp + e * K);
-            ga[e] = ((m == RN_MATCH_IGNORE) ? 0.0f : P.a_neg) * gl;  // ignored anchors contribute nothing
-            if (m >= 0) {
-                anypos = true;
-                const int blk = (s_cat[m] - c_begin) / RN_LVL_U;
-                if (s_cat[m] >= c_begin && s_cat[m] < c_end) posblocks |= (blk < 64) ? (1ull << blk) : ~0ull;
-            }
-        }
-#pragma unroll
-        for (int h = 0; h < NPK; ++h) ga2[h] = (V >= 2) ? rn_pack(ga[2 * h], ga[(2 * h + 1) % V]) : rn_splat(ga[0]);
-    }
-    if (P.cchunk > 64 * RN_LVL_U && anypos) posblocks = ~0ull;
-    const float ga_pos = P.a_pos * gl;
-
     const size_t plane0 = ((size_t)b * K + k) * C;  // first class plane of (b, k)
     const float *xp = P.clas[l] + plane0 * Pl + p;
+
+    // The first block of class planes is requested before anything else: it does not depend on the ground truth,
+    // on the assignment kernel this launch overlaps with (PDL) or on the CTA barrier below.
+    RnLv<V> xv[U];
+    auto load_block = [&](RnLv<V>(&dst)[U], int c0) {
+        const float *xq = xp + (size_t)c0 * Pl;
+#pragma unroll
+        for (int u = 0; u < U; ++u) dst[u].load(xq + u * Pl);
+    };
+    int c = c_begin;
+    bool have = valid && (c + U <= c_end);
+    if (have) load_block(xv, c);
+
+    if (threadIdx.x < 32) rn_compact_gt(P.gt_boxes + (size_t)b * P.M, P.gt_cats + (size_t)b * P.M, P.M, s_box, nullptr, s_cat);
+    rn_pdl_wait();  // launched with PDL right behind rn_assign: wait for its matches / npos
+    const int n_pos = P.npos[b];
+    const float n_norm = fmaxf((float)n_pos, 1.0f);    // clamp(min=1), Vision.py:1530
+    const float gl = __fdiv_rn(P.wc_over_bs, n_norm);  // upstream of every focal term
+    __syncthreads();                                   // s_cat / s_box visible
+    if (!valid) return;
+
+    const int32_t *mp = P.matches + (size_t)b * P.A + g.off[l] + p * K + k;  // this thread's V assignments, stride K
+    const float ga_pos = P.a_pos * gl;
     float *dp = GRAD ? P.dclas[l] + plane0 * Pl + p : nullptr;
     float *pp = (LOGITS && P.probs[l]) ? P.probs[l] + plane0 * Pl + p : nullptr;
+    auto next_block = [&]() {
+        c += U;
+        have = c + U <= c_end;
+        if (have) load_block(xv, c);
+    };
 
-    rn_f2 acc2[NPK];
+    if constexpr (G2) {
+        // gamma == 2 (the reference's default): every element is first treated as background, arithmetic packed
+        // two-wide, with nothing but the packed gradient scales and sums live across the class loop (registers: three
+        // CTAs per SM).  The thread's few positive elements (Vision.py:1588-1593) are corrected afterwards.
+        rn_f2 ga2[NPK], acc2[NPK];
+        {
+            float ga[V];
 #pragma unroll
-    for (int h = 0; h < NPK; ++h) acc2[h] = 0ull;
-
-    int c = c_begin;
-#pragma unroll 1
-    for (; c + RN_LVL_U <= c_end; c += RN_LVL_U) {
-        RnLv<V> xv[RN_LVL_U];
-        const float *xq = xp + (size_t)c * Pl;
+            for (int e = 0; e < V; ++e) ga[e] = ((__ldg(mp + e * K) == RN_MATCH_IGNORE) ? 0.0f : P.a_neg) * gl;
 #pragma unroll
-        for (int u = 0; u < RN_LVL_U; ++u) xv[u].load(xq + u * Pl);
-        float *dq = GRAD ? dp + (size_t)c * Pl : nullptr;
-        float *pq = (LOGITS && pp) ? pp + (size_t)c * Pl : nullptr;
-        const bool slow = (posblocks >> min((c - c_begin) / RN_LVL_U, 63)) & 1ull;
-        if (!slow && G2) {  // common case: every element has target 0; arithmetic packed two-wide
-            if (V >= 2) {
-#pragma unroll
-                for (int u = 0; u < RN_LVL_U; ++u) {
-                    RnLv<V> gv;
-#pragma unroll
-                    for (int h = 0; h < NPK; ++h) {
-                        float y0 = xv[u].at(2 * h), y1 = xv[u].at((2 * h + 1) % V);
-                        if (LOGITS) rn_sigmoid_pair(y0, y1, y0, y1);
-                        float g0 = 0.f, g1 = 0.f;
-                        rn_focal_pair_neg<GRAD>(y0, y1, P.lo, P.hi, ga2[h], acc2[h], g0, g1);
-                        if (LOGITS && GRAD) {  // sigmoid backward: grad * (1 - y) * y
-                            g0 = (g0 * (1.0f - y0)) * y0;
-                            g1 = (g1 * (1.0f - y1)) * y1;
-                        }
-                        gv.at(2 * h) = g0;
-                        gv.at((2 * h + 1) % V) = g1;
-                        if (LOGITS && pp) {
-                            xv[u].at(2 * h) = y0;
-                            xv[u].at((2 * h + 1) % V) = y1;
-                        }
-                    }
-                    if (LOGITS && pp) xv[u].store(pq + u * Pl);
-                    if (GRAD) gv.store(dq + u * Pl);
-                }
-            } else {  // V == 1: pair two class planes of the same cell
-#pragma unroll
-                for (int u = 0; u < RN_LVL_U; u += 2) {
-                    float y0 = xv[u].at(0), y1 = xv[u + 1].at(0);
-                    if (LOGITS) rn_sigmoid_pair(y0, y1, y0, y1);
-                    float g0 = 0.f, g1 = 0.f;
-                    rn_focal_pair_neg<GRAD>(y0, y1, P.lo, P.hi, ga2[0], acc2[0], g0, g1);
-                    if (LOGITS && GRAD) {
-                        g0 = (g0 * (1.0f - y0)) * y0;
-                        g1 = (g1 * (1.0f - y1)) * y1;
-                    }
-                    if (LOGITS && pp) {
-                        pq[u * Pl] = y0;
-                        pq[(u + 1) * Pl] = y1;
-                    }
-                    if (GRAD) {
-                        RnLv<V> gv;
-                        gv.at(0) = g0;
-                        gv.store(dq + u * Pl);
-                        gv.at(0) = g1;
-                        gv.store(dq + (u + 1) * Pl);
-                    }
-                }
-            }
-        } else {  // a positive anchor's class lies in this block (Vision.py:1588-1593), or gamma != 2
-            int pc[V];
-            float a_row[V];
-#pragma unroll
-            for (int e = 0; e < V; ++e) {
-                const int m = __ldg(mp + e * K);
-                pc[e] = m >= 0 ? s_cat[m] : -1;
-                a_row[e] = (m == RN_MATCH_IGNORE) ? 0.0f : P.a_neg;
-            }
-#pragma unroll
-            for (int u = 0; u < RN_LVL_U; ++u) {
-                RnLv<V> gv;
-#pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    float y = xv[u].at(e);
-                    if (LOGITS) {
-                        float dummy;
-                        rn_sigmoid_pair(y, y, y, dummy);
-                    }
-                    float t = 0.0f;
-                    float gq = rn_focal_elem_rt<G2, GRAD>(pc[e] == c + u, y, P, a_row[e] * gl, ga_pos, t, acc_pos);
-                    acc_neg_w = fmaf(0.5f * a_row[e], t, acc_neg_w);
-                    if (LOGITS && GRAD) gq = (gq * (1.0f - y)) * y;
-                    gv.at(e) = gq;
-                    if (LOGITS && pp) xv[u].at(e) = y;
-                }
-                if (LOGITS && pp) xv[u].store(pq + u * Pl);
-                if (GRAD) gv.store(dq + u * Pl);
+            for (int h = 0; h < NPK; ++h) {
+                ga2[h] = (V >= 2) ? rn_pack(ga[2 * h], ga[(2 * h + 1) % V]) : rn_splat(ga[0]);
+                acc2[h] = 0ull;
             }
         }
-    }
+        // two background elements: probabilities (in place), gradients, packed sum
+        auto two = [&](float &y0, float &y1, float &g0, float &g1, rn_f2 ga, rn_f2 &acc) {
+            if (LOGITS) rn_sigmoid_pair(y0, y1, y0, y1);
+            g0 = g1 = 0.0f;
+            rn_focal_pair_neg<GRAD>(y0, y1, P.lo, P.hi, ga, acc, g0, g1);
+            if (LOGITS && GRAD) {  // sigmoid backward: grad * (1 - y) * y
+                g0 = (g0 * (1.0f - y0)) * y0;
+                g1 = (g1 * (1.0f - y1)) * y1;
+            }
+        };
+        auto plane = [&](RnLv<V> &x, size_t off, rn_f2 *acc) {  // one class plane, V >= 2
+            RnLv<V> gv;
+#pragma unroll
+            for (int h = 0; h < NPK; ++h) two(x.at(2 * h), x.at((2 * h + 1) % V), gv.at(2 * h), gv.at((2 * h + 1) % V), ga2[h], acc[h]);
+            if (LOGITS && pp) x.store(pp + off);
+            if (GRAD) gv.store(dp + off);
+        };
 #pragma unroll 1
-    for (; c < c_end; ++c) {  // remainder planes (chunk length not a multiple of RN_LVL_U)
-        RnLv<V> xv, gv;
-        xv.load(xp + (size_t)c * Pl);
+        while (have) {
+            const size_t off = (size_t)c * Pl;
+            if (V >= 2) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) plane(xv[u], off + u * Pl, acc2);
+            } else {  // V == 1: pair two class planes of the same cell
+#pragma unroll
+                for (int u = 0; u < U; u += 2) {
+                    RnLv<V> g0, g1;
+                    two(xv[u].at(0), xv[u + 1].at(0), g0.at(0), g1.at(0), ga2[0], acc2[0]);
+                    if (LOGITS && pp) {
+                        xv[u].store(pp + off + u * Pl);
+                        xv[u + 1].store(pp + off + (u + 1) * Pl);
+                    }
+                    if (GRAD) {
+                        g0.store(dp + off + u * Pl);
+                        g1.store(dp + off + (u + 1) * Pl);
+                    }
+                }
+            }
+            next_block();
+        }
+        float rem1 = 0.0f;  // V == 1 only: remainder planes of the single cell
+#pragma unroll 1
+        for (; c < c_end; ++c) {  // remainder planes (chunk length not a multiple of U)
+            RnLv<V> x1;
+            x1.load(xp + (size_t)c * Pl);
+            if (V >= 2) {
+                plane(x1, (size_t)c * Pl, acc2);
+            } else {
+                RnLv<V> g0;
+                float ydup = x1.at(0), gdup, s0, s1;
+                rn_f2 t = 0ull;
+                two(x1.at(0), ydup, g0.at(0), gdup, ga2[0], t);
+                rn_unpack(t, s0, s1);
+                rem1 += s0;
+                if (LOGITS && pp) x1.store(pp + (size_t)c * Pl);
+                if (GRAD) g0.store(dp + (size_t)c * Pl);
+            }
+        }
+        // weight the per-cell sums, 0.5 * (1 - alpha) * sum(pw * -2 log q) (zero for ignored anchors), and redo the
+        // positive elements of this thread: the matched class of a positive anchor has target 1.
+        float cell_sum[V];
+#pragma unroll
+        for (int h = 0; h < NPK; ++h) {
+            float s0, s1;
+            rn_unpack(acc2[h], s0, s1);
+            if (V >= 2) {
+                cell_sum[2 * h] = s0;
+                cell_sum[(2 * h + 1) % V] = s1;
+            } else {
+                cell_sum[0] = (s0 + s1) + rem1;
+            }
+        }
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             const int m = __ldg(mp + e * K);
             const float a_row = (m == RN_MATCH_IGNORE) ? 0.0f : P.a_neg;
-            float y = xv.at(e);
-            if (LOGITS) {
-                float dummy;
-                rn_sigmoid_pair(y, y, y, dummy);
+            if (m >= 0) {
+                const int pc = s_cat[m];
+                if (pc >= c_begin && pc < c_end) {
+                    const size_t off = (size_t)pc * Pl + e;
+                    float y = __ldg(xp + off), ydup = y, gneg, gdup, s0, s1;
+                    rn_f2 t = 0ull;
+                    two(y, ydup, gneg, gdup, rn_splat(a_row * gl), t);  // exactly what the class loop added for it
+                    rn_unpack(t, s0, s1);
+                    cell_sum[e] -= s0;
+                    float tp = 0.0f;
+                    float gq = rn_focal_elem<true, true, GRAD>(y, P.lo, P.hi, P.gamma, ga_pos, tp);
+                    acc_pos = fmaf(0.5f * P.a_pos, tp, acc_pos);
+                    if (LOGITS && GRAD) gq = (gq * (1.0f - y)) * y;
+                    if (GRAD) dp[off] = gq;
+                }
             }
-            float t = 0.0f;
-            float gq = rn_focal_elem_rt<G2, GRAD>(m >= 0 && s_cat[m] == c, y, P, a_row * gl, ga_pos, t, acc_pos);
-            acc_neg_w = fmaf(0.5f * a_row, t, acc_neg_w);
-            if (LOGITS && GRAD) gq = (gq * (1.0f - y)) * y;
-            gv.at(e) = gq;
-            if (LOGITS && pp) xv.at(e) = y;
+            acc_neg_w = fmaf(0.5f * a_row, cell_sum[e], acc_neg_w);
         }
-        if (LOGITS && pp) xv.store(pp + (size_t)c * Pl);
-        if (GRAD) gv.store(dp + (size_t)c * Pl);
-    }
-    // weight the packed per-cell sums: 0.5 * (1 - alpha) * sum(pw * -2 log q), zero for ignored anchors
-    int m[V];
+    } else {
+        // general gamma: scalar element math with a run-time target
+        auto elems = [&](RnLv<V> &x, int cls, size_t off) {
+            RnLv<V> gv;
 #pragma unroll
-    for (int e = 0; e < V; ++e) m[e] = __ldg(mp + e * K);
+            for (int e = 0; e < V; ++e) {
+                const int m = __ldg(mp + e * K);
+                const float a_row = (m == RN_MATCH_IGNORE) ? 0.0f : P.a_neg;
+                float y = x.at(e);
+                if (LOGITS) {
+                    float dummy;
+                    rn_sigmoid_pair(y, y, y, dummy);
+                }
+                float t = 0.0f;
+                float gq = rn_focal_elem_rt<false, GRAD>(m >= 0 && s_cat[m] == cls, y, P, a_row * gl, ga_pos, t, acc_pos);
+                acc_neg_w = fmaf(0.5f * a_row, t, acc_neg_w);
+                if (LOGITS && GRAD) gq = (gq * (1.0f - y)) * y;
+                gv.at(e) = gq;
+                if (LOGITS && pp) x.at(e) = y;
+            }
+            if (LOGITS && pp) x.store(pp + off);
+            if (GRAD) gv.store(dp + off);
+        };
+#pragma unroll 1
+        while (have) {
 #pragma unroll
-    for (int h = 0; h < NPK; ++h) {
-        float s0, s1;
-        rn_unpack(acc2[h], s0, s1);
-        if (V >= 2) {
-            acc_neg_w = fmaf(0.5f * ((m[2 * h] == RN_MATCH_IGNORE) ? 0.0f : P.a_neg), s0, acc_neg_w);
-            acc_neg_w = fmaf(0.5f * ((m[(2 * h + 1) % V] == RN_MATCH_IGNORE) ? 0.0f : P.a_neg), s1, acc_neg_w);
-        } else {
-            acc_neg_w = fmaf(0.5f * ((m[0] == RN_MATCH_IGNORE) ? 0.0f : P.a_neg), s0 + s1, acc_neg_w);
+            for (int u = 0; u < U; ++u) elems(xv[u], c + u, (size_t)(c + u) * Pl);
+            next_block();
+        }
+#pragma unroll 1
+        for (; c < c_end; ++c) {
+            RnLv<V> x1;
+            x1.load(xp + (size_t)c * Pl);
+            elems(x1, c, (size_t)c * Pl);
         }
     }
 
@@ -270,6 +311,13 @@ __device__ __forceinline__ void rn_lvl_body(const RnLvlParams &P, const RnGeom &
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int e = 0; e < V; ++e) gj[j].at(e) = 0.0f;
+    int m[V];
+    bool anypos = false;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        m[e] = __ldg(mp + e * K);
+        anypos |= m[e] >= 0;
+    }
     if (anypos) {
         const float numel = (float)(4 * n_pos);
         const float ge = n_pos > 0 ? __fdiv_rn(P.wr_over_bs, numel) : 0.0f;  // mean() backward
@@ -317,12 +365,12 @@ __device__ __forceinline__ void rn_lvl_body(const RnLvlParams &P, const RnGeom &
 
 // grid = (tiles per image x class chunks, B).  blockIdx.x -> (row tile, class chunk), row tile -> level.
 template <bool G2, bool GRAD, bool LOGITS>
-__global__ void __launch_bounds__(RN_THREADS, 3)
+__global__ void __launch_bounds__(LOGITS ? RN_LVL_THREADS_LOGIT : RN_LVL_THREADS_PROB, LOGITS ? RN_LVL_CTAS_LOGIT : RN_LVL_CTAS_PROB)
 rn_loss_levels_kernel(const __grid_constant__ RnLvlParams P, const __grid_constant__ RnGeom g) {
     extern __shared__ __align__(16) unsigned char smem[];
     float4 *s_box = reinterpret_cast<float4 *>(smem);
     int *s_cat = reinterpret_cast<int *>(s_box + P.M);
-    __shared__ float s_red[2][RN_THREADS / 32];
+    __shared__ float s_red[2][RN_LVL_THREADS_MAX / 32];
 
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
@@ -331,19 +379,12 @@ rn_loss_levels_kernel(const __grid_constant__ RnLvlParams P, const __grid_consta
     const int l = (tile >= P.tile0[1]) + (tile >= P.tile0[2]) + (tile >= P.tile0[3]) + (tile >= P.tile0[4]);
     const int row_tile = tile - P.tile0[l];
 
-    if (tid < 32) rn_compact_gt(P.gt_boxes + (size_t)b * P.M, P.gt_cats + (size_t)b * P.M, P.M, s_box, nullptr, s_cat);
-    rn_pdl_wait();  // launched with PDL right behind rn_assign: wait for its matches / npos
-
-    const int n_pos = P.npos[b];
-    const float n_norm = fmaxf((float)n_pos, 1.0f);    // clamp(min=1), Vision.py:1530
-    const float gl = __fdiv_rn(P.wc_over_bs, n_norm);  // upstream of every focal term
-    __syncthreads();                                   // s_cat / s_box visible
-
     float acc_neg = 0.0f, acc_pos = 0.0f, acc_reg = 0.0f;
     const int V = P.V[l];
-    if (V == 4) rn_lvl_body<4, G2, GRAD, LOGITS>(P, g, b, l, row_tile, chunk, s_box, s_cat, gl, n_pos, acc_neg, acc_pos, acc_reg);
-    else if (V == 2) rn_lvl_body<2, G2, GRAD, LOGITS>(P, g, b, l, row_tile, chunk, s_box, s_cat, gl, n_pos, acc_neg, acc_pos, acc_reg);
-    else rn_lvl_body<1, G2, GRAD, LOGITS>(P, g, b, l, row_tile, chunk, s_box, s_cat, gl, n_pos, acc_neg, acc_pos, acc_reg);
+    constexpr int U = LOGITS ? RN_LVL_U_LOGIT : RN_LVL_U_PROB;
+    if (V == 4) rn_lvl_body<4, U, G2, GRAD, LOGITS>(P, g, b, l, row_tile, chunk, s_box, s_cat, acc_neg, acc_pos, acc_reg);
+    else if (V == 2) rn_lvl_body<2, U, G2, GRAD, LOGITS>(P, g, b, l, row_tile, chunk, s_box, s_cat, acc_neg, acc_pos, acc_reg);
+    else rn_lvl_body<1, U, G2, GRAD, LOGITS>(P, g, b, l, row_tile, chunk, s_box, s_cat, acc_neg, acc_pos, acc_reg);
 
     rn_pdl_trigger();
     float c = rn_warp_sum(acc_neg + acc_pos);
@@ -355,8 +396,7 @@ rn_loss_levels_kernel(const __grid_constant__ RnLvlParams P, const __grid_consta
     __syncthreads();
     if (tid == 0) {
         float cs = 0.f, rs = 0.f;
-#pragma unroll
-        for (int w = 0; w < RN_THREADS / 32; ++w) {
+        for (int w = 0; w < (int)blockDim.x / 32; ++w) {
             cs += s_red[0][w];
             rs += s_red[1][w];
         }
@@ -369,10 +409,13 @@ rn_loss_levels_kernel(const __grid_constant__ RnLvlParams P, const __grid_consta
 // ------------------------------------------------------------------------------------------------
 struct RnLvlPlan {
     int P[RN_NUM_LEVELS], V[RN_NUM_LEVELS], tile0[RN_NUM_LEVELS + 1];
-    int A, cchunk, nchunks, grid_x;
+    int A, cchunk, nchunks, grid_x, threads;
 };
 
-static void rn_lvl_plan(RnLvlPlan *pl, int B, int H, int W, int K, int C) {
+static void rn_lvl_plan(RnLvlPlan *pl, int B, int H, int W, int K, int C, bool logits) {
+    const int threads = logits ? RN_LVL_THREADS_LOGIT : RN_LVL_THREADS_PROB;
+    const int ctas = logits ? RN_LVL_CTAS_LOGIT : RN_LVL_CTAS_PROB;
+    pl->threads = threads;
     pl->A = 0;
     pl->tile0[0] = 0;
     for (int l = 0; l < RN_NUM_LEVELS; ++l) {
@@ -382,17 +425,16 @@ static void rn_lvl_plan(RnLvlPlan *pl, int B, int H, int W, int K, int C) {
         pl->P[l] = P;
         pl->V[l] = (P % 4 == 0) ? 4 : ((P % 2 == 0) ? 2 : 1);
         pl->A += K * P;
-        const int per_tile = RN_THREADS * pl->V[l];
+        const int per_tile = threads * pl->V[l];
         pl->tile0[l + 1] = pl->tile0[l] + (K * P + per_tile - 1) / per_tile;
     }
     // classes per CTA: as many as possible (the stride-K gather of the assignments and the prologue are paid once
-    // per CTA) while the grid keeps >= ~8 waves of 148 SMs x 3 resident CTAs; multiples of RN_LVL_U.
-    int cchunk = ((C + RN_LVL_U - 1) / RN_LVL_U) * RN_LVL_U;
-    while (cchunk > RN_LVL_U) {
-        const int nch = (C + cchunk - 1) / cchunk;
-        if ((long long)B * pl->tile0[RN_NUM_LEVELS] * nch >= 8LL * 148 * 3) break;
-        cchunk -= RN_LVL_U;
-    }
+    // per CTA) while the grid keeps >= ~8 waves of 148 SMs x 3 resident CTAs; chunks are balanced multiples of RN_LVL_CHUNK_Q.
+    const int blocks = (C + RN_LVL_CHUNK_Q - 1) / RN_LVL_CHUNK_Q;
+    int nch = 1;
+    while (nch < blocks && (long long)B * pl->tile0[RN_NUM_LEVELS] * nch < 8LL * 148 * ctas) ++nch;
+    if (const char *e = getenv("RN_LVL_NCHUNKS")) nch = max(1, min(blocks, atoi(e)));  // tuning override
+    int cchunk = ((blocks + nch - 1) / nch) * RN_LVL_CHUNK_Q;
     if (cchunk > C) cchunk = C;
     pl->cchunk = cchunk;
     pl->nchunks = (C + cchunk - 1) / cchunk;
@@ -401,21 +443,23 @@ static void rn_lvl_plan(RnLvlPlan *pl, int B, int H, int W, int K, int C) {
 
 extern "C" size_t rn_loss_levels_workspace_bytes(int B, int H, int W, int K, int C) {
     if (B <= 0 || H <= 0 || W <= 0 || K <= 0 || C <= 0) return 256;
-    RnLvlPlan pl;
-    rn_lvl_plan(&pl, B, H, W, K, C);
-    // worst case over the chunking heuristic: one chunk per RN_LVL_U classes
-    const size_t max_chunks = (size_t)((C + RN_LVL_U - 1) / RN_LVL_U);
-    const size_t partials = sizeof(float2) * (size_t)B * pl.tile0[RN_NUM_LEVELS] * max_chunks;
+    RnLvlPlan a, b;
+    rn_lvl_plan(&a, B, H, W, K, C, false);
+    rn_lvl_plan(&b, B, H, W, K, C, true);
+    const size_t tiles = (size_t)(a.tile0[RN_NUM_LEVELS] > b.tile0[RN_NUM_LEVELS] ? a.tile0[RN_NUM_LEVELS] : b.tile0[RN_NUM_LEVELS]);
+    // worst case over the chunking heuristic: one chunk per RN_LVL_CHUNK_Q classes
+    const size_t max_chunks = (size_t)((C + RN_LVL_CHUNK_Q - 1) / RN_LVL_CHUNK_Q);
+    const size_t partials = sizeof(float2) * (size_t)B * tiles * max_chunks;
     const size_t per_image = sizeof(float) * 2 * (size_t)B;
     return ((partials + 255) / 256) * 256 + ((per_image + 255) / 256) * 256;
 }
 
 template <bool LOGITS>
-static void rn_launch_levels(bool g2, bool grad, dim3 grid, size_t smem, cudaStream_t s, const RnLvlParams &P, const RnGeom &g) {
-    if (g2 && grad) rn_launch_pdl(rn_loss_levels_kernel<true, true, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
-    else if (g2) rn_launch_pdl(rn_loss_levels_kernel<true, false, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
-    else if (grad) rn_launch_pdl(rn_loss_levels_kernel<false, true, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
-    else rn_launch_pdl(rn_loss_levels_kernel<false, false, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
+static void rn_launch_levels(bool g2, bool grad, dim3 grid, int threads, size_t smem, cudaStream_t s, const RnLvlParams &P, const RnGeom &g) {
+    if (g2 && grad) rn_launch_pdl(rn_loss_levels_kernel<true, true, LOGITS>, grid, dim3(threads), smem, s, P, g);
+    else if (g2) rn_launch_pdl(rn_loss_levels_kernel<true, false, LOGITS>, grid, dim3(threads), smem, s, P, g);
+    else if (grad) rn_launch_pdl(rn_loss_levels_kernel<false, true, LOGITS>, grid, dim3(threads), smem, s, P, g);
+    else rn_launch_pdl(rn_loss_levels_kernel<false, false, LOGITS>, grid, dim3(threads), smem, s, P, g);
 }
 
 extern "C" int rn_loss_levels(const float *const *clas_levels, const float *const *reg_levels, int from_logits,
@@ -437,7 +481,7 @@ extern "C" int rn_loss_levels(const float *const *clas_levels, const float *cons
         return rn_set_error(RN_ERR_WORKSPACE, "rn_loss_levels: workspace needs %zu bytes, 256-byte aligned",
                             rn_loss_levels_workspace_bytes(B, H, W, K, C));
     RnLvlPlan pl;
-    rn_lvl_plan(&pl, B, H, W, K, C);
+    rn_lvl_plan(&pl, B, H, W, K, C, from_logits != 0);
     RnGeom g;
     int rc = rn_build_geom(&g, H, W, base, K, nullptr, pl.A);
     if (rc) return rc;
@@ -481,8 +525,8 @@ extern "C" int rn_loss_levels(const float *const *clas_levels, const float *cons
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(pl.grid_x, B);
     const bool g2 = (gamma == 2.0);
-    if (from_logits) rn_launch_levels<true>(g2, grad, grid, smem, s, P, g);
-    else rn_launch_levels<false>(g2, grad, grid, smem, s, P, g);
+    if (from_logits) rn_launch_levels<true>(g2, grad, grid, pl.threads, smem, s, P, g);
+    else rn_launch_levels<false>(g2, grad, grid, pl.threads, smem, s, P, g);
     rc = rn_check_launch("rn_loss_levels");
     if (rc) return rc;
     rn_launch_pdl(rn_loss_final_kernel, dim3(1), dim3(1024), 0, s, reinterpret_cast<const float2 *>(P.partials), npos, B,
