@@ -19,17 +19,19 @@
 #include "rn_loss_math.cuh"
 
 // Tuning (measured on B200, COCO B=16, A/B runs inside one gpurun call next to the flat kernel; profiles/r01_summary.md):
-// the probability variant is latency bound -- 8 planes in flight per thread, 128-thread CTAs at 6 per SM (80 registers;
-// 4 planes in flight: 0.51 ms instead of 0.42; double buffering at 2 CTAs/SM: no gain) -- and the logits variant issue
-// bound (the fused sigmoid adds ~10 instructions per element): 4 planes, 256-thread CTAs at 4 per SM (64 registers,
-// 0.496 ms; with the probability variant's shape 0.54 ms).  More class chunks per row tile are slower (the CTA
-// prologue -- ground-truth compaction, barrier, stride-K gather -- is paid per chunk): 1 chunk 0.416, 5 chunks 0.463 ms.
+// both variants wait for memory most of the time (stall_long_sb ~60 % of the samples), so the CTAs are small (128
+// threads: warps drift apart over a 40-class chunk and registers are only released per CTA) and every load of a block is
+// fenced ahead of its first consumer.  Probabilities: 8 planes in flight, 6 CTAs/SM (80 registers; 4 planes: 0.51 ms
+// instead of 0.42; double buffering at 2 CTAs/SM: no gain; 256-thread CTAs: 0.427).  Logits: 4 planes, 8 CTAs/SM
+// (64 registers, 0.487 ms; 8 planes at 6 CTAs/SM 0.53; 256-thread CTAs 0.54).  More class chunks per row tile are
+// slower (the CTA prologue -- ground-truth compaction, barrier, stride-K gather -- is paid per chunk): 1 chunk 0.416,
+// 5 chunks 0.463 ms.
 #define RN_LVL_CHUNK_Q 8  // class chunks are multiples of this
 #ifndef RN_LVL_THREADS_PROB
 #define RN_LVL_THREADS_PROB 128
 #endif
 #ifndef RN_LVL_THREADS_LOGIT
-#define RN_LVL_THREADS_LOGIT 256
+#define RN_LVL_THREADS_LOGIT 128
 #endif
 #define RN_LVL_THREADS_MAX 256
 #ifndef RN_LVL_U_PROB
@@ -42,7 +44,7 @@
 #define RN_LVL_U_LOGIT 4
 #endif
 #ifndef RN_LVL_CTAS_LOGIT
-#define RN_LVL_CTAS_LOGIT 4
+#define RN_LVL_CTAS_LOGIT 8
 #endif
 
 struct RnLvlParams {
@@ -73,6 +75,7 @@ struct RnLv<4> {
     __device__ __forceinline__ void load(const float *p) { d = rn_ldg_stream(reinterpret_cast<const float4 *>(p)); }
     __device__ __forceinline__ void store(float *p) const { rn_stg_stream(reinterpret_cast<float4 *>(p), d); }
     __device__ __forceinline__ float &at(int e) { return e == 0 ? d.x : (e == 1 ? d.y : (e == 2 ? d.z : d.w)); }
+    __device__ __forceinline__ void keep() { rn_keep_live(d); }  // scheduling fence, see rn_common.cuh
 };
 template <>
 struct RnLv<2> {
@@ -84,6 +87,7 @@ struct RnLv<2> {
         asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(d.x), "f"(d.y) : "memory");
     }
     __device__ __forceinline__ float &at(int e) { return e == 0 ? d.x : d.y; }
+    __device__ __forceinline__ void keep() { asm volatile("" : "+f"(d.x), "+f"(d.y)); }
 };
 template <>
 struct RnLv<1> {
@@ -93,6 +97,7 @@ struct RnLv<1> {
     }
     __device__ __forceinline__ void store(float *p) const { asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(d) : "memory"); }
     __device__ __forceinline__ float &at(int) { return d; }
+    __device__ __forceinline__ void keep() { asm volatile("" : "+f"(d)); }
 };
 
 // One class element with a run-time target (the rare blocks that contain a positive anchor's class).
@@ -133,6 +138,8 @@ __device__ __forceinline__ void rn_lvl_body(const RnLvlParams &P, const RnGeom &
         const float *xq = xp + (size_t)c0 * Pl;
 #pragma unroll
         for (int u = 0; u < U; ++u) dst[u].load(xq + u * Pl);
+#pragma unroll
+        for (int u = 0; u < U; ++u) dst[u].keep();  // every load of the block is issued before its first consumer
     };
     int c = c_begin;
     bool have = valid && (c + U <= c_end);
