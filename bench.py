@@ -406,9 +406,15 @@ def cpu_baseline_loss(cfg, max_images=None):
     reg = rng.standard_normal((n, A, 4), dtype=np.float32) * np.float32(0.5)
     gb, gc = syn.make_targets(n, M, H, W, C, seed=1002)
     orc.loss(an[:1024], clas[:1, :1024], reg[:1, :1024], gb.numpy()[:1], gc.numpy()[:1])  # warm the library
+    gbn, gcn = gb.numpy(), gc.numpy()
     t0 = time.perf_counter()
-    orc.loss(an, clas, reg, gb.numpy(), gc.numpy())
-    dt = time.perf_counter() - t0
+    passes = 0
+    while True:   # bounded sample: whole passes over the batch until ~2 s of wall time (x cores of CPU work)
+        orc.loss(an, clas, reg, gbn, gcn)
+        passes += 1
+        dt = time.perf_counter() - t0
+        if dt >= 2.0 or passes >= 64:
+            break
     # BASELINE.json configs[0]: the CPU-runnable case, B=2, 512x512, 20 classes, <= 10 GT boxes / image
     an1 = orc.anchors(512, 512)
     gb1, gc1 = syn.make_targets(2, 10, 512, 512, 20, seed=1001)
@@ -416,8 +422,9 @@ def cpu_baseline_loss(cfg, max_images=None):
     t1 = time.perf_counter()
     orc.loss(an1, c1.numpy(), r1.numpy(), gb1.numpy(), gc1.numpy())
     cfg1_ms = (time.perf_counter() - t1) * 1e3
-    return n / dt, min(threads, n), ("oracle port, %d COCO-shaped images (800x1344, C=80) fwd+bwd, 1 image per thread, %.1f s; "
-                                     "configs[0] (B=2, 512x512, C=20) takes %.1f ms" % (n, dt, cfg1_ms))
+    return n * passes / dt, min(threads, n), ("oracle port, %d passes over %d COCO-shaped images (800x1344, C=80) fwd+bwd, 1 image per "
+                                              "thread, %.1f s wall; configs[0] (B=2, 512x512, C=20) takes %.1f ms"
+                                              % (passes, n, dt, cfg1_ms))
 
 
 def run_ours(args):
