@@ -427,6 +427,39 @@ def cpu_baseline_loss(cfg, max_images=None):
                                               % (passes, n, dt, cfg1_ms))
 
 
+def torch_cuda_baseline(cfg, device, n=4):
+    """The reference's own sequence of torch operations (tests/torch_restatement.py, pinned bit for bit against the
+    unmodified reference on CPU) executed with torch's CUDA kernels: what the reference does on a GPU, its intended
+    mode.  The reference itself is Python and cannot travel to the GPU box.  images/s fwd+bwd."""
+    import torch
+
+    from neuralnetworklibrary_b200 import testing as syn
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator
+    from tests import torch_restatement as tr
+
+    H, W, C, M = cfg["H"], cfg["W"], cfg["C"], cfg["M"]
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=device)).clone()
+    clas, reg = device_activations(n, anchors.shape[0], C, 1009, device, mu=-4.6)
+    gb, gc = syn.make_targets(n, M, H, W, C, seed=1009)
+    gb, gc = gb.to(device), gc.to(device)
+
+    def step():
+        cl, rg = clas.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+        loss = tr.ssd_loss(anchors, rg, cl, gb, gc)[0]
+        loss.backward()
+        return loss
+
+    step()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        step()
+    torch.cuda.synchronize(device)
+    dt = time.perf_counter() - t0
+    return n * reps / dt, "%d passes over %d COCO-shaped images, torch %s CUDA kernels, per-image Python loop as in the reference" % (reps, n, torch.__version__)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -532,6 +565,12 @@ def run_ours(args):
                                      "forward and backward (not counted here)"}
             except Exception as exc:
                 line[key] = {"error": repr(exc)}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                tv, tsample = torch_cuda_baseline(COCO, device)
+                line["torch_cuda_baseline"] = {"value": round(tv, 1), "unit": "images/s", "kind": "restatement", "sample": tsample}
+            except Exception as exc:
+                line["torch_cuda_baseline"] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_baseline_loss(COCO)
             line["cpu_baseline"] = {"value": round(v, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}

@@ -117,3 +117,42 @@ def test_levels_rejects_wrong_shapes():
         SSD_loss()([anchors, [t.to(dev()) for t in reg_lv], bad], tgt)
     with pytest.raises(ValueError):
         SSD_loss()([anchors.clone(), [t.to(dev()) for t in reg_lv], [t.to(dev()) for t in clas_lv]], tgt)
+
+
+def test_levels_all_images_empty_and_other_anchor_sets():
+    """No ground truth at all (every anchor background, reg loss 0, Vision.py:1498-1501 / :1603) and an anchor set with
+    K != 9 (2 ratios x 2 scales): the level layout follows K."""
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator
+    from neuralnetworklibrary_b200.vision import SSD_loss, level_shapes
+    H, W, C, B = 96, 136, 20, 2
+    # (a) empty ground truth, default anchors
+    anchors, an, gb, gc, flat_c, flat_r, clas_lv, reg_lv, cs, rs = _setup(331, H, W, C, B, 3)
+    gb[:] = -1
+    gc[:] = -1
+    cd = [t.to(dev()).requires_grad_(True) for t in clas_lv]
+    rd = [t.to(dev()).requires_grad_(True) for t in reg_lv]
+    f = SSD_loss()
+    loss = f([anchors, rd, cd], [gb.to(dev()), gc.to(dev())])
+    loss.backward()
+    o = orc.loss(an, flat_c.numpy(), flat_r.numpy(), gb.numpy(), gc.numpy())
+    np.testing.assert_allclose(np.array([loss.item(), f.reg_loss.item(), f.clas_loss.item()], np.float32), o["out3"], rtol=RTOL, atol=0)
+    assert f.reg_loss.item() == 0.0 and all(float(t.grad.abs().sum()) == 0.0 for t in rd)
+    syn.assert_rel(orc.heads_to_flat([t.grad.cpu().numpy() for t in cd], C), o["dclas"], what="dclas")
+    # (b) K = 4
+    ratios, scales = [0.5, 2.0], [1.0, 1.5]
+    ag = AnchorGenerator(ratios, scales)
+    anchors4 = ag(torch.zeros(1, 3, H, W, device=dev()))
+    an4 = orc.anchors(H, W, ratios, scales)
+    assert np.array_equal(anchors4.cpu().numpy(), an4)
+    gb4, gc4 = syn.make_targets(B, 5, H, W, C, seed=332, min_side=10.0, max_frac=0.7)
+    fc, fr = syn.make_train_activations(B, an4.shape[0], C, seed=332, edge_cases=32)
+    cl4 = [torch.from_numpy(x).to(dev()).requires_grad_(True) for x in orc.flat_to_heads(fc.numpy(), level_shapes(H, W, 4, C))]
+    rg4 = [torch.from_numpy(x).to(dev()).requires_grad_(True) for x in orc.flat_to_heads(fr.numpy(), level_shapes(H, W, 4, 4))]
+    f4 = SSD_loss()
+    l4 = f4([anchors4, rg4, cl4], [gb4.to(dev()), gc4.to(dev())])
+    l4.backward()
+    o4 = orc.loss(an4, fc.numpy(), fr.numpy(), gb4.numpy(), gc4.numpy(), want_matches=True)
+    assert np.array_equal(f4.last_assignment[0].cpu().numpy(), o4["matches"])
+    np.testing.assert_allclose(np.array([l4.item(), f4.reg_loss.item(), f4.clas_loss.item()], np.float32), o4["out3"], rtol=RTOL, atol=0)
+    syn.assert_rel(orc.heads_to_flat([t.grad.cpu().numpy() for t in cl4], C), o4["dclas"], what="dclas K=4")
+    syn.assert_dreg_close(orc.heads_to_flat([t.grad.cpu().numpy() for t in rg4], 4), o4["dreg"])
