@@ -259,7 +259,31 @@ def time_loss_levels(cfg, B, steps, warmup, device, from_logits):
         out3 = step(warmup + k)
     t1.record()
     torch.cuda.synchronize(device)
-    return t0.elapsed_time(t1), float(out3[0].item())
+    # what this path removes from the model: the heads' sigmoid + permute(0,2,3,1).contiguous().view() and the cat over
+    # levels (retinanet.py:215-217, :258, :286-295; Vision.py:1467-1468), forward only, with torch's own kernels
+    reg, clas, _, _ = sets[0]
+    K = 9
+
+    def layout_ops():
+        c = torch.cat([(torch.sigmoid(x) if from_logits else x).permute(0, 2, 3, 1).contiguous().view(x.shape[0], -1, C) for x in clas], dim=1)
+        r = torch.cat([x.permute(0, 2, 3, 1).contiguous().view(x.shape[0], -1, 4) for x in reg], dim=1)
+        return c, r
+
+    layout_ms = None
+    try:
+        for _ in range(2):
+            layout_ops()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            layout_ops()
+        e1.record()
+        torch.cuda.synchronize(device)
+        layout_ms = e0.elapsed_time(e1) / 5
+    except Exception:
+        pass
+    return t0.elapsed_time(t1), float(out3[0].item()), layout_ms
 
 
 def time_loss_eager(anchors, sets, steps, warmup, device):
@@ -556,13 +580,15 @@ def run_ours(args):
             line["logits"] = {"error": repr(exc)}
         for key, fl in (("levels", False), ("levels_logits", True)):
             try:  # SURVEY.md section 8f row 1, second half: the loss on the heads' NCHW level tensors
-                vt, _ = time_loss_levels(COCO, B, args.steps, args.warmup, device, fl)
+                vt, _, lay = time_loss_levels(COCO, B, args.steps, args.warmup, device, fl)
                 line[key] = {"workload": "coco_loss_fwd_bwd on the heads' NCHW level tensors%s, B=%d 800x1344 C=80"
                                          % (" (logits, sigmoid fused)" if fl else "", B),
                              "images_per_s": round(B * args.steps / (vt * 1e-3), 1), "ms_per_step": round(vt / args.steps, 4),
                              "roofline_frac_whole_step": round(loss_bytes(B, A, COCO["C"]) * args.steps / (vt * 1e-3) / 1e9 / peak, 4),
-                             "note": "removes the permute/contiguous/view and cat passes over [B,A,C] from the model's "
-                                     "forward and backward (not counted here)"}
+                             "removed_head_layout_ops_fwd_ms": None if lay is None else round(lay, 4),
+                             "note": "removes the heads' %spermute/contiguous/view and the cat over levels from the model "
+                                     "(removed_head_layout_ops_fwd_ms: those torch ops, forward only, same tensors; their "
+                                     "backward is removed as well)" % ("sigmoid, " if fl else "")}
             except Exception as exc:
                 line[key] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:

@@ -19,7 +19,12 @@
 // => run-to-run bit-identical results.
 #include "rn_loss_math.cuh"
 
+#ifndef RN_LOSS_U
 #define RN_LOSS_U 8  // vectors per thread
+#endif
+#ifndef RN_LOSS_CTAS
+#define RN_LOSS_CTAS 3
+#endif
 #define RN_LOSS_TILE (RN_THREADS * RN_LOSS_U)
 
 struct RnLossParams {
@@ -150,7 +155,7 @@ __device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, const flo
 // bound ptxas drifted from 80 to 88 registers after an unrelated parameter-struct change, dropping
 // occupancy to two CTAs per SM and the kernel from 370 us to 419 us (profiles/r01_summary.md).
 template <int V, int CVT, bool G2, bool GRAD, bool LOGITS>
-__global__ void __launch_bounds__(RN_THREADS, 3)
+__global__ void __launch_bounds__(RN_THREADS, RN_LOSS_CTAS)
 rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ RnGeom g) {
     extern __shared__ __align__(16) unsigned char smem[];
     // layout: gt boxes float4[M] | gt cats int[M]

@@ -20,10 +20,10 @@ COCO, PASCAL = bench.COCO, bench.PASCAL
 A = 201600
 for w in what:
     if w in ("levels", "levels_logits"):
-        ms, _ = bench.time_loss_levels(COCO, 16, steps, 5, dev, w == "levels_logits")
+        ms, _, _ = bench.time_loss_levels(COCO, 16, steps, 5, dev, w == "levels_logits")
         out[w] = {"ms": ms / steps, "frac": bench.loss_bytes(16, A, 80) / (ms / steps * 1e-3) / 1e9 / peak}
     elif w in ("pascal_levels",):
-        ms, _ = bench.time_loss_levels(PASCAL, 32, steps, 5, dev, False)
+        ms, _, _ = bench.time_loss_levels(PASCAL, 32, steps, 5, dev, False)
         out[w] = {"ms": ms / steps, "frac": bench.loss_bytes(32, 49104, 20) / (ms / steps * 1e-3) / 1e9 / peak}
     elif w == "pascal":
         an, sets = bench.make_loss_sets(PASCAL, 32, dev, 4, 1003)
