@@ -516,6 +516,26 @@ def run_ours(args):
     e2e_steps = max(2, min(args.steps, 5))
     e2e_value = B * world * e2e_steps / (e2e_ms * 1e-3)
 
+    # BASELINE.json configs[4]: a global COCO batch of 256 images sharded by image over the ranks (all ranks take part:
+    # every step ends with the loss exchange); one input set per rank, 256/world x 64.5 MB >> L2.
+    b256 = None
+    if 256 % world == 0 and not args.no_b256:
+        try:
+            import torch
+            torch.cuda.empty_cache()
+            an256, sets256 = make_loss_sets(COCO, 256 // world, device, 1, 3002 + 1000 * rank)
+            steps256 = max(3, args.steps // 4)
+            ms256, _, _ = time_loss_graph(an256, sets256, steps256, 3, device, world)
+            del sets256
+            torch.cuda.empty_cache()
+            b256 = {"workload": "COCO shape, global batch 256 image-sharded over %d GPU(s) (%d images per GPU), loss fwd+bwd "
+                                "+ loss exchange (BASELINE configs[4])" % (world, 256 // world),
+                    "images_per_s": round(256 * steps256 / (ms256 * 1e-3), 1), "ms_per_step": round(ms256 / steps256, 4),
+                    "steps": steps256, "scaling": "strong",
+                    "roofline_frac_whole_step": round(loss_bytes(256 // world, A, COCO["C"]) * steps256 / (ms256 * 1e-3) / 1e9 / peak, 4)}
+        except Exception as exc:
+            b256 = {"error": repr(exc)}
+
     line = None
     if rank == 0:
         alg = loss_bytes(B, A, COCO["C"])
@@ -541,6 +561,8 @@ def run_ours(args):
                          "whole_step_frac": round(alg * args.steps / (total_ms * 1e-3) / 1e9 / peak, 4)},
             "clocks": clocks, "loss": last_loss,
         }
+        if b256 is not None:
+            line["coco_b256_sharded"] = b256
         # extra workloads (device-timed, single GPU share of the job): post-processing and Pascal loss
         try:
             pms, pwall, ncand, nkept, _ = time_postproc(COCO, args.postproc_batch, max(3, args.steps // 2), 3, device)
@@ -664,6 +686,7 @@ def main():
     ap.add_argument("--per-gpu-batch", type=int, default=16)
     ap.add_argument("--postproc-batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-b256", action="store_true", help="skip the BASELINE configs[4] extra (256 images over the ranks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
