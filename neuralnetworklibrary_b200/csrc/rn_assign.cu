@@ -42,9 +42,12 @@ rn_anchors_kernel(const __grid_constant__ RnGeom g, float4 *__restrict__ out) {
 //   * each thread stores its anchors' results directly: a warp writes one contiguous 4*32*KPT-byte run.
 // In table mode (caller-supplied anchors) every anchor is its own "cell" (K = 1, KT = 0).
 #define RN_ASSIGN_CELLS 64
+#ifndef RN_ASSIGN_CTAS
+#define RN_ASSIGN_CTAS 5  // resident CTAs per SM (register bound: 64 registers per thread)
+#endif
 
 template <int KT, int SPLIT>
-__global__ void __launch_bounds__(RN_ASSIGN_CELLS * SPLIT, 5)
+__global__ void __launch_bounds__(RN_ASSIGN_CELLS * SPLIT, RN_ASSIGN_CTAS)
 rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict__ gt_cats, int M,
                  const __grid_constant__ RnGeom g, const float4 *__restrict__ table, float pos_thr,
                  float neg_thr, int32_t *__restrict__ matches, int32_t *__restrict__ npos,
@@ -401,7 +404,7 @@ extern "C" int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, i
     int w_base = 11, w_box = 1;  // measured (COCO shape: 11.7 us without boxes + 1.04 us per box and image)
     if (const char *e = getenv("RN_ASSIGN_WBASE")) w_base = atoi(e) > 0 ? atoi(e) : w_base;  // tuning overrides
     const bool no_balance = getenv("RN_ASSIGN_NO_BALANCE") != nullptr;
-    const int total = 5 * 148;
+    const int total = RN_ASSIGN_CTAS * 148;
     dim3 grid;
     if (!no_balance && B > 1 && total >= 2 * B && (long long)total <= max_ctas * B && nwt >= 1024) {
         grid = dim3(total, 1);
