@@ -294,6 +294,172 @@ rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sparse assignment.  An anchor is background unless some ground-truth box reaches IoU >= neg_thr with it, and the
+// anchors that can do so with ONE box are few: their area must be within [neg_thr, 1/neg_thr] of the box's and their
+// centre close to the box's centre -- a few hundred of the 200 k anchors of a COCO-sized image.  So `matches` is filled
+// with RN_MATCH_NEG by a memset and one CTA per ground-truth box enumerates that box's candidate window on every
+// pyramid level; each candidate anchor is then evaluated EXACTLY like in the dense kernel (float32(float64 base + shift),
+// strict-fp32 IoU against all boxes of the image in ascending order, first maximal index), and written by the CTA of
+// its argmax box only, so every non-background anchor is written and counted exactly once without atomics on matches.
+//
+// Why the window is conservative.  IoU = inter/(Aa + Ag - inter) >= t  <=>  inter >= t/(1+t) * (Aa + Ag) =: need (which
+// also requires min(A) >= t*max(A)); with inter = iw*ih and ih <= min(ha, hg) this gives iw >= need/min(ha, hg) =: iw_min,
+// and since iw <= (wa+wg)/2 - |dcx| always, |dcx| <= (wa+wg)/2 - iw_min (same in y).  One window per (level, base box);
+// the kernel uses t = 0.95*neg_thr in float64 and 0.01 cell of slack, which dwarfs every rounding involved (the float32
+// rounding of the anchor coordinates is ~1e-5 px).  Anchors outside the window have IoU < neg_thr with this box, so it
+// is neither their argmax above a threshold nor able to lift them out of "background".
+// ------------------------------------------------------------------------------------------------
+#define RN_SPARSE_THREADS 256
+
+__global__ void __launch_bounds__(RN_SPARSE_THREADS)
+rn_assign_sparse_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict__ gt_cats, int M,
+                        const __grid_constant__ RnGeom g, float pos_thr, float neg_thr, int32_t *__restrict__ matches,
+                        int32_t *__restrict__ npos) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float4 *s_box = reinterpret_cast<float4 *>(smem);
+    float *s_area = reinterpret_cast<float *>(s_box + M);
+    __shared__ int s_info[2];  // valid boxes of the image, compacted index of this CTA's box
+    __shared__ int s_cnt[RN_SPARSE_THREADS / 32];
+    __shared__ int s_ix0[RN_NUM_LEVELS * RN_MAX_K], s_iy0[RN_NUM_LEVELS * RN_MAX_K], s_nw[RN_NUM_LEVELS * RN_MAX_K];
+    __shared__ int s_pref[RN_NUM_LEVELS * RN_MAX_K + 1];
+    const int b = blockIdx.y, row = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    rn_pdl_trigger();
+    const int64_t *cats = gt_cats + (size_t)b * M;
+    if (cats[row] < 0) return;  // padding row (Vision.py:1637-1638); uniform over the CTA
+    if (warp == 0) {            // compact the image's boxes (as rn_compact_gt) and find this CTA's box among them
+        const float4 *boxes = gt_boxes + (size_t)b * M;
+        int cnt = 0, self = 0;
+        for (int j0 = 0; j0 < M; j0 += 32) {
+            const int j = j0 + lane;
+            const bool valid = (j < M) && cats[j] >= 0;
+            const unsigned mask = __ballot_sync(RN_FULL_MASK, valid);
+            const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+            if (valid) {
+                const float4 bx = boxes[j];
+                s_box[pos] = bx;
+                s_area[pos] = rn_area(bx);
+                if (j == row) self = pos;
+            }
+            cnt += __popc(mask);
+        }
+        self = __reduce_max_sync(RN_FULL_MASK, self);
+        if (lane == 0) {
+            s_info[0] = cnt;
+            s_info[1] = self;
+        }
+    }
+    // ---- candidate windows: one per (level, base box), computed by warps 1.. while warp 0 compacts ----
+    const float4 me = gt_boxes[(size_t)b * M + row];
+    const double wg = (double)me.z - (double)me.x, hg = (double)me.w - (double)me.y;
+    const int K = g.K, nseg = RN_NUM_LEVELS * K;
+    for (int sg = tid - 32; sg >= 0 && sg < nseg; sg += RN_SPARSE_THREADS - 32) {
+        const int l = sg / K, k = sg - l * K;
+        int cx0 = 0, cy0 = 0, nw = 0, count = 0;
+        if (wg > 0.0 && hg > 0.0) {  // a degenerate box overlaps nothing
+            const double Ag = wg * hg, cxg = 0.5 * ((double)me.x + (double)me.z), cyg = 0.5 * ((double)me.y + (double)me.w);
+            const double tq = 0.95 * (double)neg_thr;
+            const double *bb = g.base + (l * RN_MAX_K + k) * 4;
+            const double wa = bb[2] - bb[0], ha = bb[3] - bb[1], Aa = wa * ha;
+            if (fmin(Aa, Ag) >= tq * fmax(Aa, Ag)) {       // IoU <= min(A)/max(A)
+                const double need = tq / (1.0 + tq) * (Aa + Ag);  // inter >= t/(1+t) * (Aa + Ag)
+                const double dx = 0.5 * (wa + wg) - need / fmin(ha, hg);
+                const double dy = 0.5 * (ha + hg) - need / fmin(wa, wg);
+                if (dx >= 0.0 && dy >= 0.0) {
+                    const double inv = 1.0 / (double)(8 << l);  // exact (power of two)
+                    // cells whose centre (i + 0.5) * stride lies within the distance (+ 0.01 cell of slack)
+                    const int ix0 = max(0, (int)ceil((cxg - dx) * inv - 0.51));
+                    const int ix1 = min(g.gw[l] - 1, (int)floor((cxg + dx) * inv - 0.49));
+                    const int iy0 = max(0, (int)ceil((cyg - dy) * inv - 0.51));
+                    const int iy1 = min(g.gh[l] - 1, (int)floor((cyg + dy) * inv - 0.49));
+                    if (ix1 >= ix0 && iy1 >= iy0) {
+                        cx0 = ix0;
+                        cy0 = iy0;
+                        nw = ix1 - ix0 + 1;
+                        count = nw * (iy1 - iy0 + 1);
+                    }
+                }
+            }
+        }
+        s_ix0[sg] = cx0;
+        s_iy0[sg] = cy0;
+        s_nw[sg] = nw;
+        s_pref[sg + 1] = count;
+    }
+    __syncthreads();
+    const int m = s_info[0], self = s_info[1];
+    if (warp == 0) {  // inclusive scan of the window sizes (<= 80 entries)
+        int carry = 0;
+        for (int i0 = 0; i0 < nseg; i0 += 32) {
+            const int i = i0 + lane;
+            int v = (i < nseg) ? s_pref[i + 1] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(RN_FULL_MASK, v, o);
+                if (lane >= o) v += t;
+            }
+            if (i < nseg) s_pref[i + 1] = carry + v;
+            carry += __shfl_sync(RN_FULL_MASK, v, 31);
+        }
+        if (lane == 0) s_pref[0] = 0;
+    }
+    __syncthreads();
+    const int total = s_pref[nseg];
+    int cnt = 0;
+#pragma unroll 1
+    for (int idx = tid; idx < total; idx += RN_SPARSE_THREADS) {
+        int seg = 0;  // largest seg with s_pref[seg] <= idx (binary search over <= 80 segments)
+#pragma unroll
+        for (int step = 64; step > 0; step >>= 1)
+            if (seg + step < nseg && s_pref[seg + step] <= idx) seg += step;
+        const int l = seg / K, k = seg - l * K;
+        const int local = idx - s_pref[seg], nw = s_nw[seg];
+        const int iy = s_iy0[seg] + local / nw, ix = s_ix0[seg] + local % nw;
+        const double stride = (double)(8 << l);
+        const double sx = __dmul_rn((double)ix + 0.5, stride);  // retinanet.py:458 (exact)
+        const double sy = __dmul_rn((double)iy + 0.5, stride);  // retinanet.py:459
+        const double *bb = g.base + (l * RN_MAX_K + k) * 4;
+        float4 an;
+        an.x = __double2float_rn(__dadd_rn(bb[0], sx));
+        an.y = __double2float_rn(__dadd_rn(bb[1], sy));
+        an.z = __double2float_rn(__dadd_rn(bb[2], sx));
+        an.w = __double2float_rn(__dadd_rn(bb[3], sy));
+        const float aa = rn_area(an);
+        float best = 0.0f;  // IoU >= 0 and torch.max returns index 0 for an all-zero column
+        int bi = 0;
+        for (int j = 0; j < m; ++j) {
+            const float4 gb = s_box[j];
+            const float iw = __fsub_rn(fminf(gb.z, an.z), fmaxf(gb.x, an.x));
+            const float ih = __fsub_rn(fminf(gb.w, an.w), fmaxf(gb.y, an.y));
+            if (iw > 0.0f && ih > 0.0f) {
+                const float inter = __fmul_rn(iw, ih);
+                const float uni = __fsub_rn(__fadd_rn(s_area[j], aa), inter);  // Vision.py:255
+                const float v = __fdiv_rn(inter, uni);
+                if (v > best) {  // strict: first maximal index wins (torch.max, Vision.py:1505)
+                    best = v;
+                    bi = j;
+                }
+            }
+        }
+        if (bi != self) continue;  // another box's CTA owns this anchor (or nothing overlaps it and self != 0)
+        int mt = RN_MATCH_IGNORE;
+        if (best > pos_thr) mt = bi;                 // Vision.py:1506, :1508-1509
+        else if (best < neg_thr) continue;           // background: already there (Vision.py:1507)
+        matches[(size_t)b * g.A + g.off[l] + (iy * g.gw[l] + ix) * K + k] = mt;
+        cnt += (mt >= 0);
+    }
+    cnt = __reduce_add_sync(RN_FULL_MASK, cnt);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < RN_SPARSE_THREADS / 32; ++w) t += s_cnt[w];
+        if (t) atomicAdd(npos + b, t);  // integer: order independent
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Per ground-truth row: max IoU over all anchors (jac.max(dim=1), Vision.py:1686-1687).
 __global__ void rn_max_overlaps_init_kernel(const int64_t *__restrict__ gt_cats, int n, float *__restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -387,6 +553,15 @@ extern "C" int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, i
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(npos, 0, sizeof(int32_t) * (size_t)B, s);
     if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_assign memset: %s", cudaGetErrorString(e));
+    // Sparse path (see rn_assign_sparse_kernel): generated anchors, no max-IoU output, thresholds in the usual order.
+    if (!anchors && !max_iou && M >= 1 && M <= 128 && neg_thr >= 0.2f && pos_thr >= neg_thr && !getenv("RN_ASSIGN_DENSE")) {
+        e = cudaMemsetAsync(matches, 0xff, sizeof(int32_t) * (size_t)B * (size_t)A, s);  // every anchor RN_MATCH_NEG (-1)
+        if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_assign memset: %s", cudaGetErrorString(e));
+        const size_t sm = (size_t)M * (sizeof(float4) + sizeof(float));
+        rn_assign_sparse_kernel<<<dim3(M, B), RN_SPARSE_THREADS, sm, s>>>(reinterpret_cast<const float4 *>(gt_boxes), gt_cats, M, g,
+                                                                          pos_thr, neg_thr, matches, npos);
+        return rn_check_launch("rn_assign (sparse)");
+    }
     const bool k9 = !anchors && K == 9;  // the reference's 3 ratios x 3 scales
     if (smem > 48 * 1024) {
         e = k9 ? cudaFuncSetAttribute(rn_assign_kernel<9, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
