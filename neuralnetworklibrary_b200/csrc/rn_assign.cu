@@ -311,6 +311,23 @@ rn_assign_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict_
 // ------------------------------------------------------------------------------------------------
 #define RN_SPARSE_THREADS 256
 
+// Every anchor background, every positive count zero (replaces two memset nodes; the sparse kernel behind it is
+// launched with PDL and computes its prologue while this one runs).
+__global__ void __launch_bounds__(256)
+rn_assign_fill_kernel(int32_t *__restrict__ matches, size_t n, int32_t *__restrict__ npos, int B) {
+    rn_pdl_trigger();
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    if (i0 < (size_t)B) npos[i0] = 0;  // B <= gridDim.x * 256 is checked by the host
+    if ((((uintptr_t)matches) & 15) == 0) {
+        int4 *m4 = reinterpret_cast<int4 *>(matches);
+        const int4 v = make_int4(RN_MATCH_NEG, RN_MATCH_NEG, RN_MATCH_NEG, RN_MATCH_NEG);
+        for (size_t i = i0; i < n / 4; i += stride) m4[i] = v;
+        for (size_t i = (n / 4) * 4 + i0; i < n; i += stride) matches[i] = RN_MATCH_NEG;
+    } else {
+        for (size_t i = i0; i < n; i += stride) matches[i] = RN_MATCH_NEG;
+    }
+}
+
 __global__ void __launch_bounds__(RN_SPARSE_THREADS)
 rn_assign_sparse_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict__ gt_cats, int M,
                         const __grid_constant__ RnGeom g, float pos_thr, float neg_thr, int32_t *__restrict__ matches,
@@ -406,6 +423,7 @@ rn_assign_sparse_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__re
     __syncthreads();
     const int total = s_pref[nseg];
     int cnt = 0;
+    rn_pdl_wait();  // launched with PDL behind rn_assign_fill_kernel: its background fill must be complete before we write
 #pragma unroll 1
     for (int idx = tid; idx < total; idx += RN_SPARSE_THREADS) {
         int seg = 0;  // largest seg with s_pref[seg] <= idx (binary search over <= 80 segments)
@@ -551,17 +569,20 @@ extern "C" int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, i
     size_t smem = (size_t)M * (sizeof(float4) + sizeof(float)) + sizeof(int) * (size_t)B;  // boxes | areas | image weights
     if (smem > 200 * 1024) return rn_set_error(RN_ERR_INVALID_ARG, "rn_assign: M=%d B=%d too large", M, B);
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(npos, 0, sizeof(int32_t) * (size_t)B, s);
-    if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_assign memset: %s", cudaGetErrorString(e));
     // Sparse path (see rn_assign_sparse_kernel): generated anchors, no max-IoU output, thresholds in the usual order.
     if (!anchors && !max_iou && M >= 1 && M <= 128 && neg_thr >= 0.2f && pos_thr >= neg_thr && !getenv("RN_ASSIGN_DENSE")) {
-        e = cudaMemsetAsync(matches, 0xff, sizeof(int32_t) * (size_t)B * (size_t)A, s);  // every anchor RN_MATCH_NEG (-1)
-        if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_assign memset: %s", cudaGetErrorString(e));
-        const size_t sm = (size_t)M * (sizeof(float4) + sizeof(float));
-        rn_assign_sparse_kernel<<<dim3(M, B), RN_SPARSE_THREADS, sm, s>>>(reinterpret_cast<const float4 *>(gt_boxes), gt_cats, M, g,
-                                                                          pos_thr, neg_thr, matches, npos);
-        return rn_check_launch("rn_assign (sparse)");
+        const size_t n = (size_t)B * (size_t)A;
+        const int fill_ctas = 148 * 4;
+        if (B <= fill_ctas * 256) {
+            rn_assign_fill_kernel<<<fill_ctas, 256, 0, s>>>(matches, n, npos, B);
+            const size_t sm = (size_t)M * (sizeof(float4) + sizeof(float));
+            rn_launch_pdl(rn_assign_sparse_kernel, dim3(M, B), dim3(RN_SPARSE_THREADS), sm, s,
+                          reinterpret_cast<const float4 *>(gt_boxes), gt_cats, M, g, pos_thr, neg_thr, matches, npos);
+            return rn_check_launch("rn_assign (sparse)");
+        }
     }
+    cudaError_t e = cudaMemsetAsync(npos, 0, sizeof(int32_t) * (size_t)B, s);
+    if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_assign memset: %s", cudaGetErrorString(e));
     const bool k9 = !anchors && K == 9;  // the reference's 3 ratios x 3 scales
     if (smem > 48 * 1024) {
         e = k9 ? cudaFuncSetAttribute(rn_assign_kernel<9, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)

@@ -34,6 +34,8 @@ def launches(src, dst):
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
         name = row["Kernel Name"].split("(")[0].replace("void ", "")
+        if not name.startswith("rn_"):
+            continue  # torch's kernels that generate the synthetic inputs
         v = float(row["Metric Value"].replace(",", ""))
         v = {"ns": v / 1e3, "us": v, "ms": v * 1e3}.get(row["Metric Unit"], v)
         agg.setdefault((name, row.get("Grid Size", ""), row.get("Block Size", "")), []).append(v)
