@@ -64,7 +64,11 @@ int rn_anchors(int H, int W, const double *base /*host [5][K][4]*/, int K, float
 /* jaccard + match_anchors_objects for a whole batch (Vision.py:234-256, :1474-1511, and the padding
  * strip of Vision.py:1637-1638: a ground-truth row is padding iff gt_cats < 0).
  *   gt_boxes [B,M,4] fp32, gt_cats [B,M] int64 -> matches [B,A] int32, npos [B] int32 (#positives).
- * max_iou ([B,A] fp32) may be NULL. */
+ * max_iou ([B,A] fp32) may be NULL.
+ * Two implementations with identical results: with generated anchors, max_iou == NULL, M <= 128 and
+ * 0.2 <= neg_thr <= pos_thr a background fill plus one CTA per ground-truth box over that box's candidate anchors
+ * (sparse); otherwise a dense walk over all anchors.  The environment variable RN_ASSIGN_DENSE forces the dense one
+ * (used by the tests that compare the two). */
 int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, int M, int H, int W,
               const double *base /*host*/, int K, const float *anchors /*[A,4] or NULL*/, int A,
               float pos_thr, float neg_thr, int32_t *matches, int32_t *npos, float *max_iou, void *stream);

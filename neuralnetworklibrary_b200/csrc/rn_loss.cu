@@ -17,6 +17,8 @@
 // partial per CTA, then a one-CTA final kernel (one warp per image) that sums each image's partials in a
 // fixed order in float64 and combines the images in image order.  No floating-point atomics anywhere
 // => run-to-run bit-identical results.
+#include <stdlib.h>
+
 #include "rn_loss_math.cuh"
 
 #ifndef RN_LOSS_U
@@ -298,6 +300,7 @@ static int rn_loss_iters(int B, int A, int C) {
     const long long sub = ((long long)A * (C / V) + RN_LOSS_TILE - 1) / RN_LOSS_TILE;
     int it = 4;
     while (it > 1 && (long long)B * ((sub + it - 1) / it) < 4LL * 148 * 3) it >>= 1;
+    if (const char *e = getenv("RN_LOSS_ITERS")) it = atoi(e) > 0 ? atoi(e) : it;  // tuning override
     return it;
 }
 static int rn_loss_tiles(int B, int A, int C) {  // CTAs (= partials) per image

@@ -254,7 +254,11 @@ class CapturedLossStep(object):
         self.loss, self.reg_loss, self.clas_loss = self.out3.unbind(0)
         self.dreg, self.dclas = self.bufs["dreg"], self.bufs["dclas"]
         self.matches, self.npos = self.bufs["matches"], self.bufs["npos"]
-        self.kernels_per_replay = 3  # rn_assign_kernel, rn_loss_kernel, rn_loss_final_kernel (+1 memset node)
+        # sparse assignment (generated anchors, 1 <= M <= 128, default thresholds): rn_assign_fill_kernel,
+        # rn_assign_sparse_kernel, rn_loss_kernel, rn_loss_final_kernel; dense: rn_assign_kernel (+ a memset node), loss, final
+        sparse = anchor_args(anchors)[4] is None and 1 <= int(gt_cats.shape[1]) <= 128 and cfg["neg_thresh"] >= 0.2 \
+            and cfg["pos_thresh"] >= cfg["neg_thresh"]
+        self.kernels_per_replay = 4 if sparse else 3
 
     def replay(self):
         self.graph.replay()
