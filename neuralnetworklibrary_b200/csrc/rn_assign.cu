@@ -385,10 +385,12 @@ rn_assign_sparse_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__re
                 if (dx >= 0.0 && dy >= 0.0) {
                     const double inv = 1.0 / (double)(8 << l);  // exact (power of two)
                     // cells whose centre (i + 0.5) * stride lies within the distance (+ 0.01 cell of slack)
-                    const int ix0 = max(0, (int)ceil((cxg - dx) * inv - 0.51));
-                    const int ix1 = min(g.gw[l] - 1, (int)floor((cxg + dx) * inv - 0.49));
-                    const int iy0 = max(0, (int)ceil((cyg - dy) * inv - 0.51));
-                    const int iy1 = min(g.gh[l] - 1, (int)floor((cyg + dy) * inv - 0.49));
+                    // (clamped in float64 before the conversion: a box far outside the image must not overflow an int)
+                    const double gwd = (double)g.gw[l], ghd = (double)g.gh[l];
+                    const int ix0 = (int)fmin(gwd, fmax(0.0, ceil((cxg - dx) * inv - 0.51)));
+                    const int ix1 = (int)fmin(gwd - 1.0, fmax(-1.0, floor((cxg + dx) * inv - 0.49)));
+                    const int iy0 = (int)fmin(ghd, fmax(0.0, ceil((cyg - dy) * inv - 0.51)));
+                    const int iy1 = (int)fmin(ghd - 1.0, fmax(-1.0, floor((cyg + dy) * inv - 0.49)));
                     if (ix1 >= ix0 && iy1 >= iy0) {
                         cx0 = ix0;
                         cy0 = iy0;

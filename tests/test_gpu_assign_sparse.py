@@ -88,3 +88,17 @@ def test_sparse_other_thresholds_and_anchor_sets(pos, neg):
         md, nd = _assign(anchors, gb.to(dev()), gc.to(dev()), dense=True, pos_thresh=pos, neg_thresh=neg)
         assert np.array_equal(ms, md) and np.array_equal(ns, nd)
         assert (ms != -1).sum() > 0   # the case is not vacuous
+
+
+def test_sparse_boxes_far_outside_and_non_finite():
+    """Boxes far outside the image (1e12 px), with infinite or NaN coordinates: no window, no overflow, same result as the
+    dense kernel (they overlap no anchor, or compare false everywhere)."""
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator
+    H, W = 256, 320
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=dev()))
+    gb = torch.tensor([[[40., 50., 140., 170.], [1e12, 1e12, 1e12 + 100, 1e12 + 80], [-1e12, 10., -1e12 + 50, 90.],
+                        [10., 10., float("inf"), 60.], [float("nan"), 5., 50., 60.], [100., 90., 180., 200.]]])
+    gc = torch.tensor([[1, 2, 3, 4, 5, 6]])
+    ms, ns = _assign(anchors, gb.to(dev()), gc.to(dev()), dense=False)
+    md, nd = _assign(anchors, gb.to(dev()), gc.to(dev()), dense=True)
+    assert np.array_equal(ms, md) and np.array_equal(ns, nd) and ns[0] > 0
