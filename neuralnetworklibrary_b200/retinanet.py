@@ -256,6 +256,8 @@ class BBoxPredictor(object):
     def __call__(self, img_batch, reg, clas, anchors, thresh=0.05, max_overlap=0.5,
                  rel_thresh=None, top_k=1000, max_boxes=20, dup=None, inc=None):
         bs, _, height, width = img_batch.shape
+        if isinstance(clas, (list, tuple)):
+            reg, clas = self.flatten_levels(reg, clas)
         out = self.predict_arrays(int(height), int(width), reg, clas, anchors, thresh, max_overlap, top_k,
                                   max_boxes, full=bool(rel_thresh) or bool(inc) or bool(dup))
         boxes, classes, scores, counts = out["boxes"], out["classes"], out["scores"], out["counts"]
@@ -271,6 +273,18 @@ class BBoxPredictor(object):
             PredClasses.append(list(c[:m]))
             ConfScores.append(list(s[:m]))
         return PredBoxes, PredClasses, ConfScores
+
+    from_logits = False   # set True when the model's class head returns logits (see vision.SSD_loss(from_logits=True))
+
+    def flatten_levels(self, reg_levels, clas_levels):
+        """For a model that hands over the heads' NCHW conv outputs per pyramid level (the form the level-tensor loss
+        consumes, vision.SSD_loss): the reference's layout ops (retinanet.py:215-217, :289-295; Vision.py:1467-1468) with
+        torch's kernels -- inference reads each activation once anyway, so this path is not fused."""
+        K = int(reg_levels[0].shape[1]) // 4
+        n = int(clas_levels[0].shape[1]) // K
+        reg = torch.cat([x.permute(0, 2, 3, 1).contiguous().view(x.shape[0], -1, 4) for x in reg_levels], dim=1)
+        clas = torch.cat([x.permute(0, 2, 3, 1).contiguous().view(x.shape[0], -1, n) for x in clas_levels], dim=1)
+        return reg, (torch.sigmoid(clas) if self.from_logits else clas)
 
     def predict_arrays(self, height, width, reg, clas, anchors, thresh=0.05, max_overlap=0.5, top_k=1000,
                        max_boxes=20, full=False):

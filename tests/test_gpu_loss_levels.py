@@ -156,3 +156,30 @@ def test_levels_all_images_empty_and_other_anchor_sets():
     np.testing.assert_allclose(np.array([l4.item(), f4.reg_loss.item(), f4.clas_loss.item()], np.float32), o4["out3"], rtol=RTOL, atol=0)
     syn.assert_rel(orc.heads_to_flat([t.grad.cpu().numpy() for t in cl4], C), o4["dclas"], what="dclas K=4")
     syn.assert_dreg_close(orc.heads_to_flat([t.grad.cpu().numpy() for t in rg4], 4), o4["dreg"])
+
+
+def test_predictor_accepts_level_tensors():
+    """A model that returns per-level NCHW tensors can hand them to BBoxPredictor as well: same detections as with the
+    flat tensors (the layout ops are the reference's own, retinanet.py:215-217, :289-295)."""
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator, BBoxPredictor
+    from neuralnetworklibrary_b200.vision import level_shapes
+    H, W, C, B = 128, 160, 12, 2
+    an = orc.anchors(H, W)
+    clas, reg = syn.make_infer_activations(B, an.shape[0], C, seed=341, anchors=an, mu=-5.0, clusters=6)
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=dev()))
+    img = torch.zeros(B, 3, H, W, device=dev())
+    bp = BBoxPredictor()
+    flat = bp(img, reg.to(dev()), clas.to(dev()), anchors)
+    cl = [torch.from_numpy(x).to(dev()) for x in orc.flat_to_heads(clas.numpy(), level_shapes(H, W, 9, C))]
+    rl = [torch.from_numpy(x).to(dev()) for x in orc.flat_to_heads(reg.numpy(), level_shapes(H, W, 9, 4))]
+    lv = bp(img, rl, cl, anchors)
+    for a, b in zip(flat, lv):
+        for x, y in zip(a, b):
+            assert len(x) == len(y) and all(np.array_equal(u, v) for u, v in zip(x, y))
+    assert sum(len(x) for x in flat[0]) > 0
+    # logits in: sigmoid is applied by the predictor
+    bp2 = BBoxPredictor()
+    bp2.from_logits = True
+    z = [torch.logit(t.clamp(1e-6, 1 - 1e-6)) for t in cl]
+    lz = bp2(img, rl, z, anchors)
+    assert [len(x) for x in lz[0]] == [len(x) for x in flat[0]]
