@@ -413,6 +413,51 @@ def time_postproc(cfg, B, steps, warmup, device, seed=1004):
     return dev_ms, wall_ms, int(out["n_candidates"].mean()), int(out["counts"].sum()), A
 
 
+def time_postproc_levels(cfg, B, steps, warmup, device, from_logits, seed=1011):
+    """configs[3] on the heads' NCHW level tensors (rn_postproc_levels), plus the torch layout ops it removes
+    (sigmoid if logits, permute/contiguous/view, cat) on the same tensors."""
+    import torch
+
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator, BBoxPredictor
+    from neuralnetworklibrary_b200.vision import level_shapes
+
+    H, W, C = cfg["H"], cfg["W"], cfg["C"]
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=device))
+    g = torch.Generator(device=device).manual_seed(seed)
+    clas = []
+    for shp in level_shapes(H, W, 9, C):
+        z = torch.randn((B,) + shp, generator=g, device=device) - 6.0
+        clas.append(z if from_logits else torch.sigmoid_(z))
+    reg = [torch.randn((B,) + shp, generator=g, device=device) * 0.5 for shp in level_shapes(H, W, 9, 4)]
+    bp = BBoxPredictor()
+    bp.from_logits = from_logits
+    for _ in range(warmup):
+        bp.predict_device(H, W, reg, clas, anchors)
+    torch.cuda.synchronize(device)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        bp.predict_device(H, W, reg, clas, anchors)
+    t1.record()
+    torch.cuda.synchronize(device)
+    dev_ms = t0.elapsed_time(t1) / steps
+    out = bp.predict_arrays(H, W, reg, clas, anchors)
+    lay_ms = None
+    try:
+        bp.flatten_levels(reg, clas)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            bp.flatten_levels(reg, clas)
+        e1.record()
+        torch.cuda.synchronize(device)
+        lay_ms = e0.elapsed_time(e1) / 3
+    except Exception:
+        pass
+    return dev_ms, lay_ms, int(out["n_candidates"].mean()), int(out["counts"].sum())
+
+
 def cpu_baseline_loss(cfg, max_images=None):
     """The CPU oracle on a bounded sample of the same workload (one image per host thread)."""
     import numpy as np
@@ -575,6 +620,20 @@ def run_ours(args):
                                 "roofline_frac_whole_call": round(palg / (pms / psteps * 1e-3) / 1e9 / peak, 4)}
         except Exception as exc:  # keep the headline line even if an extra fails
             line["postproc"] = {"error": repr(exc)}
+        for key, fl in (("postproc_levels", False), ("postproc_levels_logits", True)):
+            try:
+                import torch
+                torch.cuda.empty_cache()
+                lms, lay, lcand, lkept = time_postproc_levels(COCO, args.postproc_batch, max(3, args.steps // 2), 3, device, fl)
+                palg = loss_bytes(args.postproc_batch, A, COCO["C"], grad=False)
+                line[key] = {"workload": "coco_postproc on the heads' NCHW level tensors%s, B=%d 800x1344 C=80"
+                                         % (" (logits, sigmoid fused)" if fl else "", args.postproc_batch),
+                             "images_per_s": round(args.postproc_batch / (lms * 1e-3), 1), "ms_per_step": round(lms, 4),
+                             "candidates_per_image": lcand, "kept": lkept,
+                             "roofline_frac_whole_call": round(palg / (lms * 1e-3) / 1e9 / peak, 4),
+                             "removed_head_layout_ops_ms": None if lay is None else round(lay, 4)}
+            except Exception as exc:
+                line[key] = {"error": repr(exc)}
         try:
             pan, psets = make_loss_sets(PASCAL, 32, device, 4, 1003)
             pA = pan.shape[0]

@@ -160,6 +160,18 @@ int rn_postproc(const float *clas, const float *reg, int B, int A, int C, int H,
                 int32_t *anchor_idx, int32_t *counts, int32_t *n_candidates, void *workspace,
                 size_t workspace_bytes, void *stream);
 
+/* rn_postproc on the heads' NCHW level tensors (see rn_loss_levels for the layout): clas_levels / reg_levels are HOST
+ * arrays of RN_NUM_LEVELS device pointers; from_logits != 0: the class tensors hold logits, the score is
+ * sigmoid(max logit) computed like torch's CUDA sigmoid (expf + IEEE divide) and class ties are resolved on the
+ * probabilities, so the result equals torch.sigmoid + permute/view/cat + rn_postproc bit for bit while the three passes
+ * over [B,A,C] those ops cost disappear.  Generated anchors only; needs A <= 2^24 and C <= 256.  Workspace:
+ * rn_postproc_workspace_bytes(B, rn_num_anchors(H, W, K), top_k). */
+int rn_postproc_levels(const float *const *clas_levels /*host[5]*/, const float *const *reg_levels /*host[5]*/,
+                       int from_logits, int B, int C, int H, int W, const double *base /*host*/, int K,
+                       const float *mean /*host*/, const float *std /*host*/, float thresh, float max_overlap,
+                       int top_k, int max_keep, float *boxes, int64_t *classes, float *scores, int32_t *anchor_idx,
+                       int32_t *counts, int32_t *n_candidates, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Workspace for rn_nms (bytes). */
 size_t rn_nms_workspace_bytes(int n, int top_k);
 

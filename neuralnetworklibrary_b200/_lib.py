@@ -116,6 +116,9 @@ PROTOTYPES = {
     "rn_loss_levels": (C.c_int, [_pp, _pp, C.c_int, _f32p, _i64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  _f64p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, _pp, _pp, _pp, _f32p, _vp,
                                  C.c_size_t, _vp]),
+    "rn_postproc_levels": (C.c_int, [_pp, _pp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _hf32p, _hf32p,
+                                     C.c_float, C.c_float, C.c_int, C.c_int, _f32p, _i64p, _f32p, _i32p, _i32p, _i32p, _vp,
+                                     C.c_size_t, _vp]),
     "rn_map_match": (C.c_int, [_f32p, _i32p, _i32p, _f32p, _i32p, _i32p, C.c_int, C.c_int, _f32p, C.c_int, _vp, _vp]),
     "rn_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "rn_nms": (C.c_int, [_f32p, _i64p, _f32p, C.c_int, C.c_float, C.c_int, C.c_int, _i32p, _i32p, _vp,

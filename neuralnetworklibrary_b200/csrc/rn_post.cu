@@ -206,6 +206,179 @@ rn_post_scan_kernel(const float *__restrict__ clas, const float *__restrict__ re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3a on the heads' NCHW level tensors (rn_postproc_levels; SURVEY.md section 8f row 1 for inference): clas_l is
+// [B, K*C, gh_l, gw_l] with channel = k*C + c, reg_l [B, K*4, gh_l, gw_l] with channel = k*4 + j -- the conv outputs
+// without the sigmoid / permute / view / cat of retinanet.py:215-217, :258, :286-295 and Vision.py:1467-1468.
+// ------------------------------------------------------------------------------------------------
+// The four regression values of anchor a = off_l + cell*K + k of image b.
+__device__ __forceinline__ float4 rn_reg_from_levels(const RnGeom &g, const float *const *reg_lv, int b, int a) {
+    const int l = (a >= g.off[1]) + (a >= g.off[2]) + (a >= g.off[3]) + (a >= g.off[4]);
+    const int local = a - g.off[l];
+    const int cell = local / g.K, k = local - cell * g.K;
+    const size_t Pl = (size_t)g.gw[l] * g.gh[l];
+    const float *r = reg_lv[l] + (((size_t)b * g.K + k) * 4) * Pl + cell;
+    return make_float4(__ldg(r), __ldg(r + Pl), __ldg(r + 2 * Pl), __ldg(r + 3 * Pl));
+}
+
+struct RnScanLvParams {
+    const float *clas[RN_NUM_LEVELS];
+    const float *reg[RN_NUM_LEVELS];
+    int P[RN_NUM_LEVELS], V[RN_NUM_LEVELS], tile0[RN_NUM_LEVELS + 1];
+    int C, K, pack;
+    float thresh;
+    unsigned long long *keys;
+    int32_t *counts;
+};
+
+#define RN_SCANLV_THREADS 256
+#define RN_SCANLV_U 8  // class planes in flight per thread
+
+// accurate sigmoid, the operations of torch's CUDA kernel (expf + IEEE divide): the scores equal those of
+// torch.sigmoid followed by the flat path bit for bit
+__device__ __forceinline__ float rn_sigmoid_exact(float z) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-z))); }
+
+template <int V>
+struct RnPv;
+template <>
+struct RnPv<4> {
+    float4 d;
+    __device__ __forceinline__ void load(const float *p) { d = rn_ldg_stream(reinterpret_cast<const float4 *>(p)); }
+    __device__ __forceinline__ float at(int e) const { return e == 0 ? d.x : (e == 1 ? d.y : (e == 2 ? d.z : d.w)); }
+    __device__ __forceinline__ void keep() { rn_keep_live(d); }
+};
+template <>
+struct RnPv<2> {
+    float2 d;
+    __device__ __forceinline__ void load(const float *p) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(d.x), "=f"(d.y) : "l"(p));
+    }
+    __device__ __forceinline__ float at(int e) const { return e == 0 ? d.x : d.y; }
+    __device__ __forceinline__ void keep() { asm volatile("" : "+f"(d.x), "+f"(d.y)); }
+};
+template <>
+struct RnPv<1> {
+    float d;
+    __device__ __forceinline__ void load(const float *p) {
+        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(d) : "l"(p));
+    }
+    __device__ __forceinline__ float at(int) const { return d; }
+    __device__ __forceinline__ void keep() { asm volatile("" : "+f"(d)); }
+};
+
+// One thread: V consecutive cells of one (image, level, anchor slot); running (max, first argmax) over the C class
+// planes, 8 independent V*4-byte loads in flight.  LOGITS: the class tensors hold logits; the score is sigmoid(max
+// logit) -- one sigmoid per cell, not per element -- and ties are resolved on the PROBABILITIES like the reference's
+// clas.max(dim=1) (retinanet.py:759), see below.
+template <int V, bool LOGITS>
+__device__ __forceinline__ void rn_scan_lv_body(const RnScanLvParams &S, const RnGeom &g, const RnDecode &dec, int b, int l,
+                                                int row_tile, unsigned long long *s_keys, int *s_count) {
+    const int Pl = S.P[l], K = S.K, C = S.C;
+    const int r0 = (row_tile * RN_SCANLV_THREADS + threadIdx.x) * V;
+    const bool valid = r0 < K * Pl;
+    const int k = valid ? r0 / Pl : 0, p = valid ? r0 - k * Pl : 0;
+    const float *xp = S.clas[l] + ((size_t)b * K + k) * C * Pl + p;
+    float best[V], prev[V];  // running max and (LOGITS) the running max before the last take-over
+    int bc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        best[e] = -INFINITY;
+        prev[e] = -INFINITY;
+        bc[e] = 0;
+    }
+    auto update = [&](float z, int c, int e) {
+        if (z > best[e]) {  // strict: lowest class index wins ties (torch.max(dim=1), retinanet.py:759)
+            if (LOGITS) prev[e] = best[e];
+            best[e] = z;
+            bc[e] = c;
+        }
+    };
+    if (valid) {
+        int c = 0;
+#pragma unroll 1
+        for (; c + RN_SCANLV_U <= C; c += RN_SCANLV_U) {
+            RnPv<V> x[RN_SCANLV_U];
+            const float *xq = xp + (size_t)c * Pl;
+#pragma unroll
+            for (int u = 0; u < RN_SCANLV_U; ++u) x[u].load(xq + u * Pl);
+#pragma unroll
+            for (int u = 0; u < RN_SCANLV_U; ++u) x[u].keep();
+#pragma unroll
+            for (int u = 0; u < RN_SCANLV_U; ++u)
+#pragma unroll
+                for (int e = 0; e < V; ++e) update(x[u].at(e), c + u, e);
+        }
+#pragma unroll 1
+        for (; c < C; ++c) {
+            RnPv<V> x;
+            x.load(xp + (size_t)c * Pl);
+#pragma unroll
+            for (int e = 0; e < V; ++e) update(x.at(e), c, e);
+        }
+    }
+    // threshold, decode + clip, empty-box filter (retinanet.py:760-798); candidates are collected per CTA
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        float score = best[e];
+        if (LOGITS && valid) {
+            // The reference takes the max over PROBABILITIES (retinanet.py:759 after the head's sigmoid): the class is the
+            // first index whose probability equals the largest one.  sigmoid is monotonic, so that is the logit argmax
+            // unless an earlier, smaller logit rounds to the same probability; the largest earlier logit (prev) tells:
+            // only if it ties is the row scanned again (rare: saturated or nearly equal logits).
+            score = rn_sigmoid_exact(best[e]);
+            if (score > S.thresh && prev[e] > -INFINITY && rn_sigmoid_exact(prev[e]) == score) {
+                for (int c = 0; c < bc[e]; ++c)
+                    if (rn_sigmoid_exact(__ldg(xp + (size_t)c * Pl + e)) == score) {
+                        bc[e] = c;
+                        break;
+                    }
+            }
+        }
+        const int a = g.off[l] + (p + e) * K + k;
+        bool ok = valid && (score > S.thresh);  // strict, retinanet.py:760
+        if (ok) {
+            const float4 an = rn_anchor_from_param(g, nullptr, a);
+            const float4 rg = rn_reg_from_levels(g, S.reg, b, a);
+            ok = rn_box_nonempty(rn_decode(an, rg, dec));
+        }
+        const unsigned m = __ballot_sync(RN_FULL_MASK, ok);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            int basepos = 0;
+            if (lane == leader) basepos = atomicAdd(s_count, __popc(m));
+            basepos = __shfl_sync(RN_FULL_MASK, basepos, leader);
+            if (ok) s_keys[basepos + __popc(m & ((1u << lane) - 1u))] = rn_make_key(score, a, bc[e], S.pack != 0);
+        }
+    }
+}
+
+template <bool LOGITS>
+__global__ void __launch_bounds__(RN_SCANLV_THREADS)
+rn_post_scan_levels_kernel(const __grid_constant__ RnScanLvParams S, const __grid_constant__ RnGeom g,
+                           const __grid_constant__ RnDecode dec) {
+    __shared__ unsigned long long s_keys[RN_SCANLV_THREADS * 4];
+    __shared__ int s_count, s_pos;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int l = (tile >= S.tile0[1]) + (tile >= S.tile0[2]) + (tile >= S.tile0[3]) + (tile >= S.tile0[4]);
+    const int row_tile = tile - S.tile0[l];
+    const int V = S.V[l];
+    if (V == 4) rn_scan_lv_body<4, LOGITS>(S, g, dec, b, l, row_tile, s_keys, &s_count);
+    else if (V == 2) rn_scan_lv_body<2, LOGITS>(S, g, dec, b, l, row_tile, s_keys, &s_count);
+    else rn_scan_lv_body<1, LOGITS>(S, g, dec, b, l, row_tile, s_keys, &s_count);
+    rn_pdl_trigger();  // the select kernel may be scheduled as this grid's last CTAs retire
+    __syncthreads();
+    const int n = s_count;
+    if (threadIdx.x == 0 && n > 0) s_pos = atomicAdd(S.counts + b, n);
+    __syncthreads();
+    if (n > 0) {
+        unsigned long long *dst = S.keys + (size_t)b * g.A + s_pos;
+        for (int i = threadIdx.x; i < n; i += RN_SCANLV_THREADS) dst[i] = s_keys[i];
+    }
+}
+
 // Keys for caller-provided scores (rn_nms).
 __global__ void rn_make_keys_kernel(const float *__restrict__ scores, int n, unsigned long long *__restrict__ keys,
                                     int32_t *__restrict__ count) {
@@ -346,6 +519,9 @@ struct RnNmsParams {
     const float *clas, *reg;
     const float4 *table;
     int A, C, pack;
+    // level-tensor variant (rn_postproc_levels): reg_lv[l] is [B, K*4, gh_l, gw_l]; class always packed in the key
+    const float *reg_lv[RN_NUM_LEVELS];
+    int levels;
     // FROM_BOXES = true
     const float4 *boxes_in;
     const int64_t *classes_in;
@@ -408,7 +584,12 @@ rn_post_nms_kernel(const __grid_constant__ RnNmsParams P, const __grid_constant_
                 for (int c = 0; c < P.C; ++c) rn_argmax_update(__ldg(row + c), c, best, cls);
             }
             const float4 an = rn_anchor(g, s_base, P.table, a);
-            const float4 rg = __ldg(reinterpret_cast<const float4 *>(P.reg) + (size_t)b * P.A + a);
+            float4 rg;
+            if (P.levels) {
+                rg = rn_reg_from_levels(g, P.reg_lv, b, a);
+            } else {
+                rg = __ldg(reinterpret_cast<const float4 *>(P.reg) + (size_t)b * P.A + a);
+            }
             box = rn_decode(an, rg, dec);
         }
         s_box[t] = box;
@@ -579,6 +760,73 @@ extern "C" int rn_postproc(const float *clas, const float *reg, int B, int A, in
     RnNmsParams P;
     memset(&P, 0, sizeof(P));
     P.clas = clas; P.reg = reg; P.table = table; P.A = A; P.C = C; P.pack = pack;
+    P.top_k = top_k; P.max_keep = max_keep; P.max_overlap = max_overlap;
+    P.out_boxes = reinterpret_cast<float4 *>(boxes); P.out_classes = classes; P.out_scores = scores;
+    P.out_idx = anchor_idx; P.out_counts = counts; P.out_ncand = n_candidates;
+    return rn_launch_select_nms(false, B, A, P, g, dec, ws, L, s);
+}
+
+extern "C" int rn_postproc_levels(const float *const *clas_levels, const float *const *reg_levels, int from_logits, int B,
+                                  int C, int H, int W, const double *base, int K, const float *mean, const float *std,
+                                  float thresh, float max_overlap, int top_k, int max_keep, float *boxes, int64_t *classes,
+                                  float *scores, int32_t *anchor_idx, int32_t *counts, int32_t *n_candidates,
+                                  void *workspace, size_t workspace_bytes, void *stream) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0 || K > RN_MAX_K)
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc_levels: B=%d C=%d H=%d W=%d K=%d", B, C, H, W, K);
+    if (!clas_levels || !reg_levels || !base || !mean || !std || !boxes || !classes || !scores || !counts)
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc_levels: null pointer");
+    if (top_k < 1 || top_k > RN_MAX_TOP_K) return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc_levels: top_k=%d outside [1,%d]", top_k, RN_MAX_TOP_K);
+    if (max_keep < 1 || max_keep > top_k) return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc_levels: max_keep=%d outside [1,top_k=%d]", max_keep, top_k);
+    if (((uintptr_t)boxes) & 15) return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc_levels: boxes must be 16-byte aligned");
+    const int A = rn_num_anchors(H, W, K);
+    if (A > (1 << 24) || C > 256)
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc_levels: needs A <= 2^24 and C <= 256 (A=%d C=%d)", A, C);
+    const RnPostWs L = rn_post_layout(B, A, top_k);
+    if (!workspace || workspace_bytes < L.total || (((uintptr_t)workspace) & 255))
+        return rn_set_error(RN_ERR_WORKSPACE, "rn_postproc_levels: workspace needs %zu bytes, 256-byte aligned", L.total);
+    RnGeom g;
+    int rc = rn_build_geom(&g, H, W, base, K, nullptr, A);
+    if (rc) return rc;
+    RnDecode dec;
+    for (int i = 0; i < 4; ++i) {
+        dec.mean[i] = mean[i];
+        dec.std[i] = std[i];
+    }
+    dec.img_w = (float)W;  // clamp(max=width), retinanet.py:792
+    dec.img_h = (float)H;  // clamp(max=height), retinanet.py:793
+
+    RnScanLvParams S;
+    RnNmsParams P;
+    memset(&P, 0, sizeof(P));
+    S.tile0[0] = 0;
+    for (int l = 0; l < RN_NUM_LEVELS; ++l) {
+        if (!clas_levels[l] || !reg_levels[l]) return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc_levels: null level pointer (level %d)", l);
+        if ((((uintptr_t)clas_levels[l]) | ((uintptr_t)reg_levels[l])) & 15)
+            return rn_set_error(RN_ERR_INVALID_ARG, "rn_postproc_levels: level tensors must be 16-byte aligned (level %d)", l);
+        const int Pl = g.gw[l] * g.gh[l];
+        S.clas[l] = clas_levels[l];
+        S.reg[l] = reg_levels[l];
+        P.reg_lv[l] = reg_levels[l];
+        S.P[l] = Pl;
+        S.V[l] = (Pl % 4 == 0) ? 4 : ((Pl % 2 == 0) ? 2 : 1);
+        const int per_tile = RN_SCANLV_THREADS * S.V[l];
+        S.tile0[l + 1] = S.tile0[l] + (K * Pl + per_tile - 1) / per_tile;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    int32_t *d_counts = reinterpret_cast<int32_t *>(ws + L.counts);
+    cudaError_t e = cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)B, s);
+    if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_postproc_levels memset: %s", cudaGetErrorString(e));
+    S.C = C; S.K = K; S.pack = 1; S.thresh = thresh;
+    S.keys = reinterpret_cast<unsigned long long *>(ws + L.keys);
+    S.counts = d_counts;
+    const dim3 grid(S.tile0[RN_NUM_LEVELS], B);
+    if (from_logits) rn_post_scan_levels_kernel<true><<<grid, RN_SCANLV_THREADS, 0, s>>>(S, g, dec);
+    else rn_post_scan_levels_kernel<false><<<grid, RN_SCANLV_THREADS, 0, s>>>(S, g, dec);
+    rc = rn_check_launch("rn_post_scan_levels");
+    if (rc) return rc;
+
+    P.levels = 1; P.A = A; P.C = C; P.pack = 1;
     P.top_k = top_k; P.max_keep = max_keep; P.max_overlap = max_overlap;
     P.out_boxes = reinterpret_cast<float4 *>(boxes); P.out_classes = classes; P.out_scores = scores;
     P.out_idx = anchor_idx; P.out_counts = counts; P.out_ncand = n_candidates;

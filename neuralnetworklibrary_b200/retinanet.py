@@ -256,8 +256,6 @@ class BBoxPredictor(object):
     def __call__(self, img_batch, reg, clas, anchors, thresh=0.05, max_overlap=0.5,
                  rel_thresh=None, top_k=1000, max_boxes=20, dup=None, inc=None):
         bs, _, height, width = img_batch.shape
-        if isinstance(clas, (list, tuple)):
-            reg, clas = self.flatten_levels(reg, clas)
         out = self.predict_arrays(int(height), int(width), reg, clas, anchors, thresh, max_overlap, top_k,
                                   max_boxes, full=bool(rel_thresh) or bool(inc) or bool(dup))
         boxes, classes, scores, counts = out["boxes"], out["classes"], out["scores"], out["counts"]
@@ -277,9 +275,9 @@ class BBoxPredictor(object):
     from_logits = False   # set True when the model's class head returns logits (see vision.SSD_loss(from_logits=True))
 
     def flatten_levels(self, reg_levels, clas_levels):
-        """For a model that hands over the heads' NCHW conv outputs per pyramid level (the form the level-tensor loss
-        consumes, vision.SSD_loss): the reference's layout ops (retinanet.py:215-217, :289-295; Vision.py:1467-1468) with
-        torch's kernels -- inference reads each activation once anyway, so this path is not fused."""
+        """The reference's layout ops (retinanet.py:215-217, :258, :286-295; Vision.py:1467-1468) with torch's kernels:
+        per-level NCHW conv outputs -> ([B,A,4], [B,A,C] probabilities).  Not used by the predictor itself (which reads
+        the level tensors directly, rn_postproc_levels); kept for callers that want the flat tensors."""
         K = int(reg_levels[0].shape[1]) // 4
         n = int(clas_levels[0].shape[1]) // K
         reg = torch.cat([x.permute(0, 2, 3, 1).contiguous().view(x.shape[0], -1, 4) for x in reg_levels], dim=1)
@@ -291,7 +289,7 @@ class BBoxPredictor(object):
         """The array form of __call__: dict of host numpy arrays boxes [B,K,4] f32, classes [B,K] i64,
         scores [B,K] f32, anchor_idx [B,K] i32 (the NMS keep indices), counts [B], n_candidates [B]."""
         dev_out = self.predict_device(height, width, reg, clas, anchors, thresh, max_overlap, top_k, max_boxes, full)
-        B = int(clas.shape[0])
+        B = int((clas[0] if isinstance(clas, (list, tuple)) else clas).shape[0])
         if dev_out is None:
             return dict(boxes=np.zeros((B, 0, 4), np.float32), classes=np.zeros((B, 0), np.int64),
                         scores=np.zeros((B, 0), np.float32), anchor_idx=np.zeros((B, 0), np.int32),
@@ -314,6 +312,8 @@ class BBoxPredictor(object):
                        max_boxes=20, full=False):
         """Launches rn_postproc on the current stream and returns (uint8 device buffer, K) without any
         host synchronisation (None when nothing can be returned); predict_arrays() decodes the buffer."""
+        if isinstance(clas, (list, tuple)):
+            return self._predict_device_levels(height, width, reg, clas, anchors, thresh, max_overlap, top_k, max_boxes, full)
         _lib.require_cuda(clas, "clas", torch.float32)
         _lib.require_cuda(reg, "reg", torch.float32)
         clas, reg = clas.detach().contiguous(), reg.detach().contiguous()
@@ -337,6 +337,49 @@ class BBoxPredictor(object):
             _lib.check(lib.rn_postproc(
                 _lib.ptr(clas), _lib.ptr(reg), B, A, Cn, height, width,
                 base, Kc, table, self._mean.ctypes.data_as(_lib._hf32p), self._std.ctypes.data_as(_lib._hf32p),
+                float(thresh), float(max_overlap), top_k, K,
+                C.c_void_p(p + o_box), C.c_void_p(p + o_cls), C.c_void_p(p + o_sc), C.c_void_p(p + o_idx),
+                C.c_void_p(p + o_cnt), C.c_void_p(p + o_cand), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+        return buf, K
+
+    def _predict_device_levels(self, height, width, reg_levels, clas_levels, anchors, thresh, max_overlap, top_k, max_boxes,
+                               full):
+        """predict_device for a model that hands over the heads' NCHW conv outputs per pyramid level (reg_l [B, K*4, gh,
+        gw], clas_l [B, K*C, gh, gw]; logits when self.from_logits): rn_postproc_levels reads them as they are -- no
+        sigmoid / permute / view / cat pass (retinanet.py:215-217, :258, :286-295; Vision.py:1467-1468)."""
+        H, W, base, Kc, table, A = anchor_args(anchors, height, width)
+        if table is not None:
+            raise ValueError("level tensors need anchors from this package's AnchorGenerator (geometry tag)")
+        if len(reg_levels) != _lib.NUM_LEVELS or len(clas_levels) != _lib.NUM_LEVELS:
+            raise ValueError("expected %d level tensors (P3..P7)" % _lib.NUM_LEVELS)
+        if int(clas_levels[0].shape[1]) % Kc:
+            raise ValueError("class head channels must be a multiple of the %d anchors per cell" % Kc)
+        B, Cn = int(clas_levels[0].shape[0]), int(clas_levels[0].shape[1]) // Kc
+        clas_levels = [t.detach() for t in clas_levels]
+        reg_levels = [t.detach() for t in reg_levels]
+        for l, (c, r) in enumerate(zip(clas_levels, reg_levels)):
+            gh, gw = -(-H // (8 << l)), -(-W // (8 << l))
+            _lib.require_cuda(c, "clas level", torch.float32)
+            _lib.require_cuda(r, "reg level", torch.float32)
+            if tuple(c.shape) != (B, Kc * Cn, gh, gw) or tuple(r.shape) != (B, Kc * 4, gh, gw) or not c.is_contiguous() \
+                    or not r.is_contiguous():
+                raise ValueError("level %d: expected contiguous NCHW clas %s and reg %s" % (l, (B, Kc * Cn, gh, gw), (B, Kc * 4, gh, gw)))
+        top_k = int(top_k)
+        dev = clas_levels[0].device
+        if top_k < 1 or (not full and int(max_boxes) < 1) or B == 0:
+            return None
+        if top_k > _lib.MAX_TOP_K:
+            raise ValueError("top_k > %d is not supported" % _lib.MAX_TOP_K)
+        K = top_k if full else min(int(max_boxes), top_k)
+        lib = _lib.load()
+        o_box, o_cls, o_sc, o_idx, o_cnt, o_cand, total = self._layout(B, K)
+        with torch.cuda.device(dev):
+            buf = torch.empty(total, dtype=torch.uint8, device=dev)
+            ws = _ws.get(lib.rn_postproc_workspace_bytes(B, A, top_k), dev)
+            p = buf.data_ptr()
+            _lib.check(lib.rn_postproc_levels(
+                _lib.ptr_array(clas_levels), _lib.ptr_array(reg_levels), int(bool(self.from_logits)), B, Cn, H, W, base, Kc,
+                self._mean.ctypes.data_as(_lib._hf32p), self._std.ctypes.data_as(_lib._hf32p),
                 float(thresh), float(max_overlap), top_k, K,
                 C.c_void_p(p + o_box), C.c_void_p(p + o_cls), C.c_void_p(p + o_sc), C.c_void_p(p + o_idx),
                 C.c_void_p(p + o_cnt), C.c_void_p(p + o_cand), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))

@@ -34,6 +34,10 @@ for w in what:
         an, sets = bench.make_loss_sets(COCO, 16, dev, 2, 1005, logits=(w == "logits"))
         ms, _, _ = bench.time_loss_graph(an, sets, steps, 5, dev, 1, from_logits=(w == "logits"))
         out[w] = {"ms": ms / steps, "frac": bench.loss_bytes(16, A, 80) / (ms / steps * 1e-3) / 1e9 / peak}
+    elif w in ("postproc_levels", "postproc_levels_logits"):
+        ms, lay, ncand, nkept = bench.time_postproc_levels(COCO, 64, steps, 3, dev, w.endswith("logits"))
+        out[w] = {"ms": ms, "layout_ops_ms": lay, "cand": ncand, "kept": nkept,
+                  "frac": bench.loss_bytes(64, A, 80, grad=False) / (ms * 1e-3) / 1e9 / peak}
     elif w == "postproc":
         pms, pwall, ncand, nkept, _ = bench.time_postproc(COCO, 64, steps, 3, dev)
         out[w] = {"ms": pms / steps, "wall_ms": pwall / steps, "frac": bench.loss_bytes(64, A, 80, grad=False) / (pms / steps * 1e-3) / 1e9 / peak}

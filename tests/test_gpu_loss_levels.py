@@ -158,28 +158,74 @@ def test_levels_all_images_empty_and_other_anchor_sets():
     syn.assert_dreg_close(orc.heads_to_flat([t.grad.cpu().numpy() for t in rg4], 4), o4["dreg"])
 
 
-def test_predictor_accepts_level_tensors():
-    """A model that returns per-level NCHW tensors can hand them to BBoxPredictor as well: same detections as with the
-    flat tensors (the layout ops are the reference's own, retinanet.py:215-217, :289-295)."""
+@pytest.mark.parametrize("seed,H,W,C,B,mu,kw", [(341, 128, 160, 12, 2, -5.0, {}), (342, 100, 167, 80, 2, -5.5, dict(thresh=0.1, max_overlap=0.4, top_k=300, max_boxes=50)),
+                                                (343, 256, 320, 20, 3, -5.0, dict(top_k=64, max_boxes=64)), (344, 800, 1344, 80, 1, -6.0, {})])
+def test_predictor_on_level_tensors(seed, H, W, C, B, mu, kw):
+    """rn_postproc_levels (BBoxPredictor called with the heads' per-level NCHW tensors) against the flat path of this
+    library and the oracle: candidate counts, keep indices, classes, scores and boxes identical.  With logits in, the
+    flat path is fed torch.sigmoid(logits) -- the fused sigmoid uses the same operations, so everything stays bit-equal."""
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator, BBoxPredictor
+    from neuralnetworklibrary_b200.vision import level_shapes
+    an = orc.anchors(H, W)
+    clas, reg = syn.make_infer_activations(B, an.shape[0], C, seed=seed, anchors=an, mu=mu, clusters=6)
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=dev()))
+    bp = BBoxPredictor()
+    flat = bp.predict_arrays(H, W, reg.to(dev()), clas.to(dev()), anchors, **kw)
+    cl = [torch.from_numpy(x).to(dev()) for x in orc.flat_to_heads(clas.numpy(), level_shapes(H, W, 9, C))]
+    rl = [torch.from_numpy(x).to(dev()) for x in orc.flat_to_heads(reg.numpy(), level_shapes(H, W, 9, 4))]
+    lv = bp.predict_arrays(H, W, rl, cl, anchors, **kw)
+    po = orc.postproc(clas.numpy(), reg.numpy(), an, H, W, **kw)
+    assert np.array_equal(lv["counts"], po["counts"]) and np.array_equal(lv["n_candidates"], po["n_candidates"])
+    for key in ("counts", "n_candidates"):
+        assert np.array_equal(flat[key], lv[key])
+    for i in range(B):
+        n = int(flat["counts"][i])
+        for key in ("anchor_idx", "classes", "scores"):
+            assert np.array_equal(flat[key][i, :n], lv[key][i, :n]), key
+        assert np.array_equal(flat["boxes"][i, :n].view(np.uint32), lv["boxes"][i, :n].view(np.uint32))
+        assert np.array_equal(lv["anchor_idx"][i, :n], po["anchor_idx"][i, :n])
+    assert int(flat["counts"].sum()) > 0
+    # logits in
+    z = [torch.randn_like(t) * 1.5 + mu for t in cl]
+    for t in z:                                     # plant confident clusters so that NMS has something to do
+        t.view(-1)[:: max(1, t.numel() // 97)] += 9.0
+    # probability ties between different logits: saturated logits (sigmoid == 1.0) and neighbours one ulp apart, with
+    # the smaller logit at the LOWER class index -- torch.max over probabilities keeps that lower index
+    z0 = z[0].view(B, 9, C, -1)
+    z0[:, 0, 1, 0], z0[:, 0, C - 1, 0] = 20.0, 25.0
+    z0[:, 1, 2, 1], z0[:, 1, 3, 1] = 17.5, 18.5
+    z0[:, 2, 0, 2] = 3.0
+    z0[:, 2, 4, 2] = torch.nextafter(torch.tensor(3.0), torch.tensor(4.0)).item()
+    bz = BBoxPredictor()
+    bz.from_logits = True
+    lz = bz.predict_arrays(H, W, rl, z, anchors, **kw)
+    _, probs = bz.flatten_levels(rl, z)             # torch.sigmoid + the reference's layout ops
+    fz = bp.predict_arrays(H, W, reg.to(dev()), probs, anchors, **kw)
+    assert np.array_equal(fz["counts"], lz["counts"]) and np.array_equal(fz["n_candidates"], lz["n_candidates"])
+    for i in range(B):
+        n = int(fz["counts"][i])
+        for key in ("anchor_idx", "classes", "scores"):
+            assert np.array_equal(fz[key][i, :n], lz[key][i, :n]), key
+        assert np.array_equal(fz["boxes"][i, :n].view(np.uint32), lz["boxes"][i, :n].view(np.uint32))
+    assert int(lz["counts"].sum()) > 0
+
+
+def test_predictor_call_accepts_level_tensors():
+    """The list-returning __call__ (what Learner.predict consumes) with level tensors."""
     from neuralnetworklibrary_b200.retinanet import AnchorGenerator, BBoxPredictor
     from neuralnetworklibrary_b200.vision import level_shapes
     H, W, C, B = 128, 160, 12, 2
     an = orc.anchors(H, W)
-    clas, reg = syn.make_infer_activations(B, an.shape[0], C, seed=341, anchors=an, mu=-5.0, clusters=6)
+    clas, reg = syn.make_infer_activations(B, an.shape[0], C, seed=345, anchors=an, mu=-5.0, clusters=6)
     anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=dev()))
     img = torch.zeros(B, 3, H, W, device=dev())
     bp = BBoxPredictor()
     flat = bp(img, reg.to(dev()), clas.to(dev()), anchors)
     cl = [torch.from_numpy(x).to(dev()) for x in orc.flat_to_heads(clas.numpy(), level_shapes(H, W, 9, C))]
     rl = [torch.from_numpy(x).to(dev()) for x in orc.flat_to_heads(reg.numpy(), level_shapes(H, W, 9, 4))]
-    lv = bp(img, rl, cl, anchors)
-    for a, b in zip(flat, lv):
+    lv = bp(img, rl, cl, anchors, 0.05, 0.5, [0.3, 0.6], 1000, 20, None, None)   # with a host stage (rel_thresh)
+    fl = bp(img, reg.to(dev()), clas.to(dev()), anchors, 0.05, 0.5, [0.3, 0.6], 1000, 20, None, None)
+    for a, b in zip(fl, lv):
         for x, y in zip(a, b):
             assert len(x) == len(y) and all(np.array_equal(u, v) for u, v in zip(x, y))
     assert sum(len(x) for x in flat[0]) > 0
-    # logits in: sigmoid is applied by the predictor
-    bp2 = BBoxPredictor()
-    bp2.from_logits = True
-    z = [torch.logit(t.clamp(1e-6, 1 - 1e-6)) for t in cl]
-    lz = bp2(img, rl, z, anchors)
-    assert [len(x) for x in lz[0]] == [len(x) for x in flat[0]]
