@@ -213,7 +213,7 @@ def time_loss_levels(cfg, B, steps, warmup, device, from_logits):
 
     from neuralnetworklibrary_b200 import testing as syn
     from neuralnetworklibrary_b200.retinanet import AnchorGenerator
-    from neuralnetworklibrary_b200.vision import _launch_loss_levels, level_shapes
+    from neuralnetworklibrary_b200.vision import SSD_loss, level_shapes
 
     H, W, C, M = cfg["H"], cfg["W"], cfg["C"], cfg["M"]
     anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=device))
@@ -227,24 +227,9 @@ def time_loss_levels(cfg, B, steps, warmup, device, from_logits):
         reg = [torch.randn((B,) + shp, generator=g, device=device) * 0.5 for shp in level_shapes(H, W, 9, 4)]
         gb, gc = syn.make_targets(B, M, H, W, C, seed=1007 + k)
         sets.append((reg, clas, gb.to(device), gc.to(device)))
-    run_cfg = dict(alpha=0.25, gamma=2.0, beta=0.5, pos_thresh=0.5, neg_thresh=0.4, world_size=1, group=None,
-                   global_batch=B, from_logits=from_logits)
-
-    # one CUDA graph per input set (assign + level loss + final reduction; outputs live in the graph's pool)
-    graphs, outs = [], []
-    side = torch.cuda.Stream(device=device)
-    side.wait_stream(torch.cuda.current_stream(device))
-    with torch.cuda.stream(side):
-        for reg, clas, gb, gc in sets:
-            _launch_loss_levels(anchors, reg, clas, gb, gc, run_cfg, True)
-    torch.cuda.current_stream(device).wait_stream(side)
-    torch.cuda.synchronize(device)
-    for reg, clas, gb, gc in sets:
-        gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr):
-            res = _launch_loss_levels(anchors, reg, clas, gb, gc, run_cfg, True)
-        graphs.append(gr)
-        outs.append(res)
+    loss_fn = SSD_loss(global_batch=B, from_logits=from_logits)
+    graphs = [loss_fn.capture([anchors, reg, clas], [gb, gc]) for reg, clas, gb, gc in sets]   # one CUDA graph per input set
+    outs = [(gr.out3,) for gr in graphs]
 
     def step(k):
         graphs[k % 2].replay()

@@ -265,6 +265,32 @@ class CapturedLossStep(object):
         return self.loss
 
 
+class CapturedLevelLossStep(object):
+    """CapturedLossStep for the level-tensor loss: the static inputs are the per-level NCHW lists handed to
+    SSD_loss.capture(); after replay() `.loss/.reg_loss/.clas_loss`, `.dreg_levels`, `.dclas_levels` (lists in the layout of
+    their inputs) and `.matches`, `.npos` hold the results (their buffers live in the graph's memory pool)."""
+
+    def __init__(self, cfg, anchors, reg_levels, clas_levels, gt_boxes, gt_cats):
+        dev = clas_levels[0].device
+        self.inputs = (anchors, reg_levels, clas_levels, gt_boxes, gt_cats)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):   # warm-up outside capture (workspace allocation, lazy module load)
+            _launch_loss_levels(anchors, reg_levels, clas_levels, gt_boxes, gt_cats, cfg, True)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out3, self.dreg_levels, self.dclas_levels, self.matches, self.npos = _launch_loss_levels(
+                anchors, reg_levels, clas_levels, gt_boxes, gt_cats, cfg, True)
+        self.loss, self.reg_loss, self.clas_loss = self.out3.unbind(0)
+        self.kernels_per_replay = 4   # rn_assign_fill_kernel, rn_assign_sparse_kernel, rn_loss_levels_kernel, rn_loss_final_kernel
+
+    def replay(self):
+        self.graph.replay()
+        return self.loss
+
+
 def reduce_loss_scalars(out3, group=None):
     """The one collective of the path: sums the three per-rank loss scalars over the image shards.
     all_gather + one fixed-order sum over the rank axis (not all_reduce), so the result is bit-identical on
@@ -350,11 +376,17 @@ class SSD_loss(object):
         """Captures forward+backward for the given static tensors into a CUDA graph (single-GPU loss
         only; the multi-GPU scalar exchange stays outside the graph).  Returns a CapturedLossStep."""
         anchors, reg, clas = activ[0], activ[1], activ[2]
-        _lib.require_cuda(reg, "reg", torch.float32)
-        _lib.require_cuda(clas, "clas", torch.float32)
         BBoxes, Cats = target[0], target[1]
         _lib.require_cuda(BBoxes, "BBoxes", torch.float32)
         _lib.require_cuda(Cats, "Cats", torch.int64)
+        if isinstance(clas, (list, tuple)):   # per-level NCHW tensors (see _call_levels)
+            if not (BBoxes.is_contiguous() and Cats.is_contiguous()):
+                raise ValueError("capture() needs contiguous static tensors")
+            cfg = self._cfg_for_call()
+            cfg.update(world_size=1, group=None, want_probs=False)
+            return CapturedLevelLossStep(cfg, anchors, [t.detach() for t in reg], [t.detach() for t in clas], BBoxes, Cats)
+        _lib.require_cuda(reg, "reg", torch.float32)
+        _lib.require_cuda(clas, "clas", torch.float32)
         for t in (reg, clas, BBoxes, Cats):
             if not t.is_contiguous():
                 raise ValueError("capture() needs contiguous static tensors")

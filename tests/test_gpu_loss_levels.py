@@ -229,3 +229,28 @@ def test_predictor_call_accepts_level_tensors():
         for x, y in zip(a, b):
             assert len(x) == len(y) and all(np.array_equal(u, v) for u, v in zip(x, y))
     assert sum(len(x) for x in flat[0]) > 0
+
+
+def test_levels_capture_replay():
+    """SSD_loss.capture() with per-level lists: graph replays reproduce the eager result and follow the static inputs."""
+    from neuralnetworklibrary_b200.vision import SSD_loss
+    anchors, an, gb, gc, flat_c, flat_r, clas_lv, reg_lv, cs, rs = _setup(351, 128, 160, 20, 2, 6)
+    cd, rd = [t.to(dev()) for t in clas_lv], [t.to(dev()) for t in reg_lv]
+    gbd, gcd = gb.to(dev()), gc.to(dev())
+    f = SSD_loss()
+    step = f.capture([anchors, rd, cd], [gbd, gcd])
+    step.replay()
+    ce = [t.clone().requires_grad_(True) for t in cd]
+    re_ = [t.clone().requires_grad_(True) for t in rd]
+    le = f([anchors, re_, ce], [gbd, gcd])
+    le.backward()
+    assert step.loss.item() == le.item()
+    for a, b in zip(step.dclas_levels, ce):
+        assert torch.equal(a, b.grad)
+    for a, b in zip(step.dreg_levels, re_):
+        assert torch.equal(a, b.grad)
+    cd[0].mul_(0.5)                      # new data in the static inputs
+    step.replay()
+    with torch.no_grad():
+        l2 = f([anchors, rd, cd], [gbd, gcd])
+    assert step.loss.item() == l2.item() and step.loss.item() != le.item()
