@@ -115,8 +115,8 @@ __device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, const flo
             if (V == 4 && G2) {
                 rn_f2 acc2 = 0ull;  // (+0.0f, +0.0f)
                 const rn_f2 ga2 = rn_splat(ga);
-                rn_focal_pair_neg<GRAD>(y[0], y[1], P.lo, P.hi, ga2, acc2, gv.at(0), gv.at(1));
-                rn_focal_pair_neg<GRAD>(y[2], y[3], P.lo, P.hi, ga2, acc2, gv.at(2), gv.at(3));
+                rn_focal_pair_neg<GRAD, LOGITS>(y[0], y[1], P.lo, P.hi, ga2, acc2, gv.at(0), gv.at(1));
+                rn_focal_pair_neg<GRAD, LOGITS>(y[2], y[3], P.lo, P.hi, ga2, acc2, gv.at(2), gv.at(3));
                 float s0, s1;
                 rn_unpack(acc2, s0, s1);
                 part = s0 + s1;
@@ -141,7 +141,7 @@ __device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, const flo
 #pragma unroll
             for (int e = 0; e < V; ++e) pp[e] = y[e];
         }
-        if (LOGITS && GRAD) {  // sigmoid backward: grad * (1 - y) * y
+        if (LOGITS && GRAD && !(V == 4 && G2 && !slow)) {  // sigmoid backward: grad * (1 - y) * y (the packed path chains itself)
 #pragma unroll
             for (int e = 0; e < V; ++e) gv.at(e) = (gv.at(e) * (1.0f - y[e])) * y[e];
         }

@@ -125,8 +125,11 @@ __device__ __forceinline__ void rn_sigmoid_pair(float z0, float z1, float &y0, f
 
 // Two background (target 0) class elements with gamma == 2: same mathematics as
 // rn_focal_elem<false, true, GRAD>, arithmetic packed two-wide.  acc2 accumulates pw * (-2 log q); ga2 holds the two
-// elements' gradient scales.
-template <bool GRAD>
+// elements' gradient scales.  CHAIN (logits variants): x0, x1 are sigmoid outputs y and the returned gradient is the
+// one w.r.t. the LOGIT.  For a pass-through element (p == y) 1 - y is the q computed here, so
+//   dl/dz = [pw/q + u*l2] * (1 - y) * y = u * (u + q*l2) * y        (pw = u*u)
+// needs no reciprocal at all; the others are zeroed by the clamp mask either way.
+template <bool GRAD, bool CHAIN = false>
 __device__ __forceinline__ void rn_focal_pair_neg(float x0, float x1, float lo, float hi, rn_f2 ga2, rn_f2 &acc2,
                                                   float &g0, float &g1) {
     const float p0 = fminf(fmaxf(x0, lo), hi), p1 = fminf(fmaxf(x1, lo), hi);  // Vision.py:1524
@@ -155,7 +158,9 @@ __device__ __forceinline__ void rn_focal_pair_neg(float x0, float x1, float lo, 
     acc2 = rn_fma2(pw, l2, acc2);
     if (!GRAD) return;
     // dl/dp / (alpha weight) = pw / q - 2 u log q = pw * rcp(q) + u * l2
-    rn_f2 g = rn_fma2(u, l2, rn_mul2(pw, rn_pack(rn_rcp_approx(q0), rn_rcp_approx(q1))));
+    rn_f2 g;
+    if (CHAIN) g = rn_mul2(rn_mul2(u, rn_fma2(q, l2, u)), rn_pack(x0, x1));
+    else g = rn_fma2(u, l2, rn_mul2(pw, rn_pack(rn_rcp_approx(q0), rn_rcp_approx(q1))));
     g = rn_mul2(g, ga2);
     rn_unpack(g, g0, g1);
     g0 = (p0 == x0) ? g0 : 0.0f;  // clamp backward: pass-through iff lo <= x <= hi (inclusive)
