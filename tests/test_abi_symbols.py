@@ -42,3 +42,37 @@ def test_sass_is_sm100a_without_fma_contraction_in_iou():
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_argument_validation_returns_error_codes_without_a_device():
+    """Bad arguments are rejected before any CUDA call: RN_ERR_INVALID_ARG / RN_ERR_WORKSPACE plus a message, never a crash
+    (the reference reports bad arguments as ValueError, Learner.py:339-340; the wrappers map these codes to it)."""
+    lib = _lib.load()
+    INVALID, WORKSPACE = _lib.RN_ERR_INVALID_ARG, _lib.RN_ERR_WORKSPACE
+    null5 = (ctypes.c_void_p * 5)()
+    assert lib.rn_loss(None, None, None, None, None, None, 0, 0, 0, 0, 0, 0, None, 9, None, 0.25, 2.0, 0.5, 1,
+                       None, None, None, None, 0, None) == INVALID
+    assert b"rn_loss" in lib.rn_last_error()
+    assert lib.rn_loss(None, None, None, None, None, None, 2, 100, 20, 4, 64, 64, None, 9, None, 0.25, 2.0, 0.5, 2,
+                       None, None, None, None, 0, None) == INVALID                     # null pointers
+    assert lib.rn_loss_levels(None, None, 0, None, None, None, None, 2, 20, 4, 64, 64, None, 9, 0.25, 2.0, 0.5, 2,
+                              None, None, None, None, None, 0, None) == INVALID
+    assert lib.rn_loss_levels(null5, null5, 0, None, None, None, None, 2, 20, 4, 64, 64, None, 99, 0.25, 2.0, 0.5, 2,
+                              None, None, None, None, None, 0, None) == INVALID        # K > RN_MAX_K
+    assert lib.rn_postproc(None, None, 1, 100, 20, 64, 64, None, 9, None, None, None, 0.05, 0.5, 1000, 20,
+                           None, None, None, None, None, None, None, 0, None) == INVALID
+    assert lib.rn_postproc_levels(None, None, 0, 1, 20, 64, 64, None, 9, None, None, 0.05, 0.5, 1000, 20,
+                                  None, None, None, None, None, None, None, 0, None) == INVALID
+    assert lib.rn_nms(None, None, None, -1, 0.5, 10, 10, None, None, None, 0, None) == INVALID
+    assert lib.rn_map_match(None, None, None, None, None, None, 1, 1, None, 0, None, None) == INVALID
+    assert lib.rn_assign(None, None, 2, 4, 64, 64, None, 9, None, 100, 0.5, 0.4, None, None, None, None) == INVALID
+    # top_k outside the supported range, workspace too small
+    import numpy as np
+    f4 = (ctypes.c_float * 4)(0, 0, 0, 0)
+    dummy = ctypes.c_void_p(256)   # non-null, 256-byte aligned; never dereferenced: validation fails first
+    assert lib.rn_postproc(dummy, dummy, 1, 100, 20, 64, 64, None, 9, dummy, f4, f4, 0.05, 0.5, 100000, 20,
+                           dummy, dummy, dummy, None, dummy, None, dummy, 1 << 30, None) == INVALID
+    base = np.zeros((5, 9, 4), np.float64)
+    assert lib.rn_loss(dummy, dummy, dummy, dummy, dummy, dummy, 2, lib.rn_num_anchors(64, 64, 9), 20, 4, 64, 64,
+                       _lib.base_ptr(base), 9, None, 0.25, 2.0, 0.5, 2, None, None, dummy, dummy, 16, None) == WORKSPACE
+    assert b"workspace" in lib.rn_last_error()
