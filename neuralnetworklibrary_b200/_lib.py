@@ -16,7 +16,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 # RETINA_B200_LIB overrides the library path (A/B comparisons of builds); the default is the in-tree build.
 LIB_PATH = os.environ.get("RETINA_B200_LIB") or os.path.join(_PKG, "libretina_sm100.so")
-SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_loss_levels.cu", "rn_post.cu"]
+SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_loss_levels.cu", "rn_loss_tma.cu", "rn_post.cu"]
 BUILD_DIR = os.path.join(_PKG, "csrc", "_build")   # object files (git-ignored); the .so is what travels
 
 NVCC_FLAGS = [

@@ -29,39 +29,6 @@
 #endif
 #define RN_LOSS_TILE (RN_THREADS * RN_LOSS_U)
 
-struct RnLossParams {
-    const float *clas;
-    const float *reg;
-    const float4 *gt_boxes;
-    const int64_t *gt_cats;
-    const int32_t *matches;
-    const int32_t *npos;
-    const float4 *table;
-    float *dclas;
-    float *dreg;
-    float *probs;     // LOGITS only, may be NULL: sigmoid(logits) as used by the kernel (for checking / reuse)
-    float *partials;  // [B][tiles][2] : {sum of focal terms, sum of smooth-L1 terms}
-    int B, A, C, CV, M, tiles, iters;
-    float a_pos, a_neg, gamma, lo, hi;
-    float wc_over_bs, wr_over_bs;  // beta / B_global, (1-beta) / B_global   (Vision.py:1644)
-};
-
-template <int V>
-struct RnVec;
-template <>
-struct RnVec<4> {
-    float4 d;
-    __device__ __forceinline__ void load(const float *p) { d = rn_ldg_stream(reinterpret_cast<const float4 *>(p)); }
-    __device__ __forceinline__ void store(float *p) const { rn_stg_stream(reinterpret_cast<float4 *>(p), d); }
-    __device__ __forceinline__ float &at(int e) { return e == 0 ? d.x : (e == 1 ? d.y : (e == 2 ? d.z : d.w)); }
-};
-template <>
-struct RnVec<1> {
-    float d;
-    __device__ __forceinline__ void load(const float *p) { d = __ldg(p); }
-    __device__ __forceinline__ void store(float *p) const { *p = d; }
-    __device__ __forceinline__ float &at(int) { return d; }
-};
 
 // One sub-tile of RN_LOSS_TILE vectors: U independent 128-bit loads per thread are issued first, then
 // the element math, then the stores.  FULL = the sub-tile lies completely inside the image, so there is
@@ -400,7 +367,9 @@ static int rn_loss_impl(bool logits, float *probs, const float *clas, const floa
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(tiles, B);
     const bool g2 = (gamma == 2.0), grad = dclas != nullptr;
-    if (logits) {
+    // experimental shared-memory staged variant (rn_loss_tma.cu), opt-in
+    if (V == 4 && getenv("RN_LOSS_TMA") && rn_launch_loss_tma(logits, g2, grad, grid, s, P, g)) {
+    } else if (logits) {
         if (V == 4 && C == 80) rn_launch_loss<4, 20, true>(g2, grad, grid, smem, s, P, g);
         else if (V == 4 && C == 20) rn_launch_loss<4, 5, true>(g2, grad, grid, smem, s, P, g);
         else if (V == 4) rn_launch_loss<4, 0, true>(g2, grad, grid, smem, s, P, g);
