@@ -16,9 +16,6 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 # RETINA_B200_LIB overrides the library path (A/B comparisons of builds); the default is the in-tree build.
 LIB_PATH = os.environ.get("RETINA_B200_LIB") or os.path.join(_PKG, "libretina_sm100.so")
-# Link order matters for speed, not only for tidiness: the level-tensor loss kernels run 4 % (probabilities) to 11 %
-# (logits) faster when their object is linked last -- measured A/B with identical objects, i.e. an effect of where the
-# ~13 KB hot loops land in the module image (profiles/r01_summary.md).
 SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_loss_tma.cu", "rn_post.cu", "rn_loss_levels.cu"]
 BUILD_DIR = os.path.join(_PKG, "csrc", "_build")   # object files (git-ignored); the .so is what travels
 
