@@ -88,6 +88,13 @@ int rn_stage_targets(const double *boxes, const int64_t *cats, const int32_t *of
                      double rand_scale, int row_jit, int col_jit, int B, int M, float *out_boxes,
                      int64_t *out_cats, void *stream);
 
+/* The pixel half of AspectRatioCollater after its cv2.resize (Vision.py:775-777 jitter placement, :786 HWC -> CHW,
+ * :790-796 zero padding to the batch's common size): pixels holds the images' float32 HWC data back to back, offsets [B]
+ * int64 the first element of each image, dims [B][2] int32 its (rows, cols) -- all DEVICE, one ragged upload.
+ * out [B, C, Hp, Wp] fp32: out[b, c, y, x] = img_b[y - row_jit, x - col_jit, c] inside the image, 0 elsewhere. */
+int rn_stage_images(const float *pixels, const int64_t *offsets, const int32_t *dims, int B, int C, int Hp, int Wp,
+                    int row_jit, int col_jit, float *out, void *stream);
+
 /* Workspace for rn_loss (bytes; 256-byte aligned base required). */
 size_t rn_loss_workspace_bytes(int B, int A, int C);
 

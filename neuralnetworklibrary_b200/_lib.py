@@ -100,6 +100,7 @@ PROTOTYPES = {
     "rn_max_overlaps": (C.c_int, [_f32p, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _f32p, C.c_int,
                                   _f32p, _vp]),
     "rn_stage_targets": (C.c_int, [_vp, _i64p, _i32p, _vp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _i64p, _vp]),
+    "rn_stage_images": (C.c_int, [_f32p, _i64p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _vp]),
     "rn_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rn_loss": (C.c_int, [_f32p, _f32p, _f32p, _i64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                           C.c_int, _f64p, C.c_int, _f32p, C.c_double, C.c_double, C.c_double, C.c_int,

@@ -542,6 +542,27 @@ __global__ void rn_stage_targets_kernel(const double *__restrict__ boxes, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Image staging: the pixel half of AspectRatioCollater after its cv2.resize (Vision.py:775-777 jitter placement,
+// :786 HWC -> CHW, :790-796 zero padding of every image to the batch's common 32-multiple size), from one ragged upload.
+// out[b, c, y, x] = img_b[y - row_jit, x - col_jit, c] inside the image, 0 elsewhere.  Pure data movement: bit exact.
+__global__ void __launch_bounds__(256)
+rn_stage_images_kernel(const float *__restrict__ pixels, const int64_t *__restrict__ offsets, const int32_t *__restrict__ dims,
+                       int C, int Hp, int Wp, int row_jit, int col_jit, float *__restrict__ out) {
+    const int b = blockIdx.z, y = blockIdx.y;
+    const int rows = dims[2 * b], cols = dims[2 * b + 1];
+    const float *src = pixels + offsets[b];
+    const int sy = y - row_jit;
+    const bool row_in = sy >= 0 && sy < rows;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * Wp; i += gridDim.x * blockDim.x) {
+        const int c = i / Wp, x = i - c * Wp;
+        const int sx = x - col_jit;
+        float v = 0.0f;
+        if (row_in && sx >= 0 && sx < cols) v = __ldg(src + ((size_t)sy * cols + sx) * C + c);
+        out[(((size_t)b * C + c) * Hp + y) * Wp + x] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
 static const size_t kBaseBytes = sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4;
@@ -647,4 +668,15 @@ extern "C" int rn_stage_targets(const double *boxes, const int64_t *cats, const 
         boxes, cats, offsets, scales, rand_scale, (double)row_jit, (double)col_jit, B, M,
         reinterpret_cast<float4 *>(out_boxes), out_cats);
     return rn_check_launch("rn_stage_targets");
+}
+
+extern "C" int rn_stage_images(const float *pixels, const int64_t *offsets, const int32_t *dims, int B, int C, int Hp, int Wp,
+                               int row_jit, int col_jit, float *out, void *stream) {
+    if (B <= 0 || C <= 0 || Hp <= 0 || Wp <= 0 || Hp > 65535 || B > 65535)
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_stage_images: B=%d C=%d Hp=%d Wp=%d", B, C, Hp, Wp);
+    if (!pixels || !offsets || !dims || !out) return rn_set_error(RN_ERR_INVALID_ARG, "rn_stage_images: null pointer");
+    const int per_row = C * Wp;
+    dim3 grid((per_row + 255) / 256 > 8 ? 8 : (per_row + 255) / 256, Hp, B);
+    rn_stage_images_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pixels, offsets, dims, C, Hp, Wp, row_jit, col_jit, out);
+    return rn_check_launch("rn_stage_images");
 }

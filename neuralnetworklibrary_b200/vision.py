@@ -510,6 +510,49 @@ def stage_targets(bboxes, cats, scales, rand_scale=1.0, row_jit=0, col_jit=0, de
     return [out_boxes, out_cats]
 
 
+def stage_images(images, row_jit=0, col_jit=0, device=None):
+    """Device-side version of the pixel half of AspectRatioCollater after its cv2.resize (reference Vision.py:775-777,
+    :786, :790-796): every (already resized) H x W x C image is placed at (row_jit, col_jit), transposed to C x H x W and
+    zero-padded to the batch's common size, height and width rounded up to multiples of 32 -- from ONE pinned, ragged
+    host->device upload and one kernel instead of two padded host arrays and a transpose per batch.  Returns a float32
+    tensor [bs, C, H, W] on the device (what the reference hands to to_cuda)."""
+    lib = _lib.load()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    B = len(images)
+    if B == 0:
+        raise ValueError("stage_images needs at least one image")
+    shapes = [tuple(int(d) for d in np.shape(im)) for im in images]
+    if any(len(s) != 3 or s[2] != shapes[0][2] for s in shapes):
+        raise ValueError("images must be H x W x C arrays with the same number of channels")
+    Cn = shapes[0][2]
+    row_jit, col_jit = int(row_jit), int(col_jit)
+    Hp = int(32 * np.ceil(max(s[0] + row_jit for s in shapes) / 32))     # Vision.py:790-792
+    Wp = int(32 * np.ceil(max(s[1] + col_jit for s in shapes) / 32))
+    sizes = [s[0] * s[1] * Cn for s in shapes]
+    offsets = np.zeros(B, dtype=np.int64)
+    offsets[1:] = np.cumsum(sizes)[:-1]
+    total = int(sum(sizes))
+    # one pinned staging buffer: pixels f32 [total] | offsets i64 [B] | dims i32 [B,2]
+    npx, nof, ndm = 4 * total, 8 * B, 8 * B
+    pad = (-npx) % 8
+    host = torch.empty(npx + pad + nof + ndm, dtype=torch.uint8, pin_memory=True)
+    hv = host.numpy()
+    px = hv[:npx].view(np.float32)
+    for i, im in enumerate(images):
+        px[offsets[i]:offsets[i] + sizes[i]] = np.asarray(im).astype(np.float32, copy=False).reshape(-1)   # Vision.py:776
+    hv[npx + pad:npx + pad + nof].view(np.int64)[:] = offsets
+    hv[npx + pad + nof:].view(np.int32)[:] = np.array([[s[0], s[1]] for s in shapes], dtype=np.int32).reshape(-1)
+    with torch.cuda.device(device):
+        dev_buf = host.to(device, non_blocking=True)
+        out = torch.empty((B, Cn, Hp, Wp), dtype=torch.float32, device=device)
+        p = dev_buf.data_ptr()
+        import ctypes as C
+        _lib.check(lib.rn_stage_images(C.c_void_p(p), C.c_void_p(p + npx + pad), C.c_void_p(p + npx + pad + nof), B, Cn, Hp, Wp,
+                                       row_jit, col_jit, _lib.ptr(out), _lib.stream_ptr(device)))
+        dev_buf.record_stream(torch.cuda.current_stream(device))
+    return out
+
+
 def merge_tta_predictions(passes, max_overlap=0.5, rel_thresh=None, top_k=1000, max_boxes=20, dup=None, inc=None):
     """The merge step of ImageLearner.TTA_bbox (reference Vision.py:2104-2119): `passes` is a list (one entry per
     augmentation pass) of per-image [boxes, classes, scores] lists already mapped back to the original image; the

@@ -280,3 +280,20 @@ def flat_to_heads(flat, level_shapes):
         a0 += rows
     assert a0 == flat.shape[1]
     return out
+
+
+def stage_images(images, row_jit=0, col_jit=0):
+    """numpy restatement of the pixel half of AspectRatioCollater after its cv2.resize (reference Vision.py:775-777
+    jitter placement, :786 transpose, :790-796 padding).  Returns imgs_padded [bs, C, H, W] float32."""
+    out = []
+    for img in images:
+        rows, cols, channels = img.shape
+        new_img = np.zeros((rows + row_jit, cols + col_jit, channels)).astype(np.float32)
+        new_img[row_jit:, col_jit:, :] = img.astype(np.float32)
+        out.append(new_img.transpose(2, 0, 1))
+    max_h = int(32 * np.ceil(max(x.shape[1] for x in out) / 32))
+    max_w = int(32 * np.ceil(max(x.shape[2] for x in out) / 32))
+    padded = np.zeros((len(out), out[0].shape[0], max_h, max_w)).astype(np.float32)
+    for i, x in enumerate(out):
+        padded[i, :, :x.shape[1], :x.shape[2]] = x
+    return padded

@@ -193,6 +193,33 @@ def gen_collater():
     np.savez_compressed(os.path.join(OUT, "collater_targets.npz"), **d)
 
 
+def image_cases():
+    """Small ragged image batches for the collater's pixel half: (images HxWx3 uint8 / float32, row_jit, col_jit)."""
+    rng = np.random.RandomState(55)
+    cases = []
+    for bs, (rj, cj) in ((3, (0, 0)), (4, (5, 11)), (1, (16, 0)), (2, (3, 30))):
+        imgs = []
+        for i in range(bs):
+            h, w = int(rng.randint(20, 90)), int(rng.randint(20, 120))
+            im = rng.randint(0, 256, size=(h, w, 3))
+            imgs.append(im.astype(np.uint8) if i % 2 else (im / 255.0).astype(np.float32))
+        cases.append((imgs, rj, cj))
+    return cases
+
+
+def gen_collater_images():
+    """Pixel half of the reference's AspectRatioCollater (Vision.py:730-797) with scale = rand_scale = 1, where its
+    cv2.resize to the image's own size is an exact copy: what remains is the jitter placement, transpose and padding."""
+    from oracle import ref_shim
+    _, vis = ref_shim.load()
+    d = {}
+    for k, (imgs, rj, cj) in enumerate(image_cases()):
+        batch = [(im.copy(), 1.0, 1.0, rj, cj, np.array([]), np.array([])) for im in imgs]
+        out, _ = vis.AspectRatioCollater(batch)
+        d["case%d" % k] = out.numpy()
+    np.savez_compressed(os.path.join(OUT, "collater_images.npz"), **d)
+
+
 def map_cases():
     """Validation-set predictions / targets for the mAP fixture: jittered copies of the ground truth plus random
     boxes; images without predictions or without targets; exact duplicates (first-argmax tie) and tied scores."""
@@ -266,6 +293,7 @@ if __name__ == "__main__":
     gen_nms_boxes()
     gen_collater()
     gen_map()
+    gen_collater_images()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

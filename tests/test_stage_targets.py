@@ -73,3 +73,36 @@ def test_merge_tta_predictions_equals_nms_of_union():
         keep = orc.nms(np.stack(b), np.array(c), np.array(s), max_boxes=50)
         assert np.array_equal(np.array(merged[l][2], np.float32), np.array(s, np.float32)[keep])
         assert np.array_equal(np.stack(merged[l][0]), np.stack(b)[keep])
+
+
+def _image_cases():
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg.image_cases()
+
+
+def test_oracle_matches_reference_collater_images(golden_dir):
+    """Pixel half of the collater (Vision.py:775-777, :786, :790-796): numpy oracle vs the reference-generated golden."""
+    g = np.load(os.path.join(golden_dir, "collater_images.npz"))
+    for k, (imgs, rj, cj) in enumerate(_image_cases()):
+        out = orc.stage_images(imgs, rj, cj)
+        assert out.dtype == np.float32 and np.array_equal(out, g["case%d" % k])
+
+
+@pytest.mark.gpu
+def test_kernel_matches_reference_collater_images(golden_dir):
+    from neuralnetworklibrary_b200.vision import stage_images
+    g = np.load(os.path.join(golden_dir, "collater_images.npz"))
+    for k, (imgs, rj, cj) in enumerate(_image_cases()):
+        out = stage_images(imgs, rj, cj)
+        assert out.is_cuda and out.dtype == torch.float32
+        assert np.array_equal(out.cpu().numpy(), g["case%d" % k])
+    # a COCO-sized batch against the oracle (the reference's own collater needs cv2 and seconds per batch)
+    rng = np.random.RandomState(3)
+    imgs = [rng.rand(int(rng.randint(600, 801)), int(rng.randint(900, 1334)), 3).astype(np.float32) for _ in range(4)]
+    out = stage_images(imgs, 7, 13)
+    assert out.shape[2] % 32 == 0 and out.shape[3] % 32 == 0
+    assert np.array_equal(out.cpu().numpy(), orc.stage_images(imgs, 7, 13))
+    with pytest.raises(ValueError):
+        stage_images([])
