@@ -254,3 +254,21 @@ def test_levels_capture_replay():
     with torch.no_grad():
         l2 = f([anchors, rd, cd], [gbd, gcd])
     assert step.loss.item() == l2.item() and step.loss.item() != le.item()
+
+
+def test_predictor_levels_no_detections_and_bad_shapes():
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator, BBoxPredictor
+    from neuralnetworklibrary_b200.vision import level_shapes
+    H, W, C, B = 96, 128, 8, 2
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=dev()))
+    cl = [torch.full((B,) + shp, 0.01, device=dev()) for shp in level_shapes(H, W, 9, C)]
+    rl = [torch.zeros((B,) + shp, device=dev()) for shp in level_shapes(H, W, 9, 4)]
+    img = torch.zeros(B, 3, H, W, device=dev())
+    boxes, classes, scores = BBoxPredictor()(img, rl, cl, anchors)          # nothing over the threshold
+    assert boxes == [[], []] and classes == [[], []] and scores == [[], []]
+    bad = list(cl)
+    bad[1] = bad[1][:, :, :, :-1].contiguous()
+    with pytest.raises(ValueError):
+        BBoxPredictor()(img, rl, bad, anchors)
+    with pytest.raises(ValueError):
+        BBoxPredictor()(img, rl, cl, anchors.clone())                      # a copy carries no geometry tag
