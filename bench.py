@@ -130,7 +130,7 @@ def loss_bytes(B, A, C, grad=True):
 def make_loss_sets(cfg, B, device, nbuf, seed, logits=False):
     import torch
 
-    from neuralnetworklibrary_b200 import testing as syn
+    from tests import synth as syn
     from neuralnetworklibrary_b200.retinanet import AnchorGenerator
 
     H, W, C, M = cfg["H"], cfg["W"], cfg["C"], cfg["M"]
@@ -211,7 +211,7 @@ def time_loss_levels(cfg, B, steps, warmup, device, from_logits):
     replays; 2 rotating input sets (each larger than L2)."""
     import torch
 
-    from neuralnetworklibrary_b200 import testing as syn
+    from tests import synth as syn
     from neuralnetworklibrary_b200.retinanet import AnchorGenerator
     from neuralnetworklibrary_b200.vision import SSD_loss, level_shapes
 
@@ -325,7 +325,7 @@ def time_loss_e2e(cfg, B, steps, warmup, device, world, seed=1002):
     import torch
     import torch.distributed as dist
 
-    from neuralnetworklibrary_b200 import testing as syn
+    from tests import synth as syn
     from neuralnetworklibrary_b200.retinanet import AnchorGenerator
     from neuralnetworklibrary_b200.vision import SSD_loss
 
@@ -447,7 +447,7 @@ def cpu_baseline_loss(cfg, max_images=None):
     """The CPU oracle on a bounded sample of the same workload (one image per host thread)."""
     import numpy as np
 
-    from neuralnetworklibrary_b200 import testing as syn
+    from tests import synth as syn
     from oracle import oracle as orc
 
     H, W, C, M = cfg["H"], cfg["W"], cfg["C"], cfg["M"]
@@ -481,13 +481,132 @@ def cpu_baseline_loss(cfg, max_images=None):
                                               % (passes, n, dt, cfg1_ms))
 
 
+def _reference_loss_inputs(cfg, n, seed=1002):
+    """n COCO-shaped images as host tensors (numpy RNG; the same generator the C port's baseline uses)."""
+    import numpy as np
+    import torch
+
+    from oracle import oracle as orc
+    from tests import synth as syn
+
+    H, W, C, M = cfg["H"], cfg["W"], cfg["C"], cfg["M"]
+    an = orc.anchors(H, W)
+    A = an.shape[0]
+    rng = np.random.default_rng(seed)
+    clas = (1.0 / (1.0 + np.exp(-(rng.standard_normal((n, A, C), dtype=np.float32) - np.float32(4.6))))).astype(np.float32)
+    reg = rng.standard_normal((n, A, 4), dtype=np.float32) * np.float32(0.5)
+    gb, gc = syn.make_targets(n, M, H, W, C, seed=seed)
+    return torch.from_numpy(an), torch.from_numpy(clas), torch.from_numpy(reg), gb, gc
+
+
+def reference_available():
+    from oracle import ref_shim
+    return ref_shim.available()
+
+
+def reference_cpu_loss(cfg, n, steps, warmup):
+    """THE REFERENCE ITSELF (unmodified sources, oracle/_ref or /root/reference): SSD_loss(...)(activ, target) +
+    loss.backward() (Applications/Vision.py:1607-1644, General/Learner.py:513-514) on the host cores, torch CPU kernels
+    with all intra-op threads, `steps` passes over n COCO-shaped images.  Returns (images/s, threads, seconds)."""
+    import torch
+
+    from oracle import ref_shim
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    an, clas, reg, gb, gc = _reference_loss_inputs(cfg, n)
+    with ref_shim.cpu_mode():
+        _, vis = ref_shim.load()
+        f = vis.SSD_loss()
+
+        def step():
+            cl, rg = clas.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+            loss = f([an, rg, cl], [gb, gc])
+            loss.backward()
+            return float(loss.item())
+
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            last = step()
+        dt = time.perf_counter() - t0
+    return n * steps / dt, torch.get_num_threads(), dt, last
+
+
+def reference_cuda_loss(cfg, device, n=4, reps=3):
+    """The unmodified reference in its intended mode: the same call, tensors and model outputs on the B200, torch's CUDA
+    kernels (per-image Python loop, ~2 host syncs per image).  images/s fwd+bwd."""
+    import torch
+
+    from oracle import ref_shim
+
+    _, vis = ref_shim.load()
+    an, clas, reg, gb, gc = (t.to(device) for t in _reference_loss_inputs(cfg, n, seed=1009))
+    f = vis.SSD_loss()
+
+    def step():
+        cl, rg = clas.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+        loss = f([an, rg, cl], [gb, gc])
+        loss.backward()
+        return loss
+
+    step()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    torch.cuda.synchronize(device)
+    dt = time.perf_counter() - t0
+    return n * reps / dt, "%d passes over %d COCO-shaped images; the unmodified reference (Vision.py:1607-1644 + autograd) on cuda, torch %s" % (reps, n, torch.__version__)
+
+
+def parity_check(anchors, cap_set, device):
+    """Outside the timed region: the FIRST timed batch (same device tensors the graph replays) against the CPU oracle --
+    assignment of every anchor of every image bit-exact, positive counts equal, the three loss scalars rtol 1e-5, and the
+    gradients of the first and last image rtol 1e-5 (scaled for dreg, host libm).  Returns a dict for the JSON line."""
+    import numpy as np
+    import torch
+
+    from neuralnetworklibrary_b200.vision import SSD_loss
+    from oracle import oracle as orc
+    from tests import synth as syn
+
+    clas, reg, gb, gc = cap_set
+    B, A, C = clas.shape
+    H, W = anchors._rn_geom.H, anchors._rn_geom.W
+    cd, rd = clas.detach().clone().requires_grad_(True), reg.detach().clone().requires_grad_(True)
+    f = SSD_loss()
+    loss = f([anchors, rd, cd], [gb, gc])
+    loss.backward()
+    matches, npos = f.last_assignment
+    got3 = np.array([loss.item(), f.reg_loss.item(), f.clas_loss.item()], np.float32)
+    an = orc.anchors(H, W)
+    o = orc.loss(an, clas.cpu().numpy(), reg.cpu().numpy(), gb.cpu().numpy(), gc.cpu().numpy(), want_matches=True)
+    ok_m = bool(np.array_equal(matches.cpu().numpy(), o["matches"]))
+    ok_n = bool(np.array_equal(npos.cpu().numpy(), o["npos"])) if "npos" in o else bool(
+        np.array_equal(npos.cpu().numpy(), (o["matches"] >= 0).sum(axis=1)))
+    rel3 = float(np.max(np.abs(got3.astype(np.float64) - o["out3"]) / np.abs(o["out3"])))
+    ok_g = True
+    try:
+        for i in (0, B - 1):
+            syn.assert_rel(cd.grad[i].cpu().numpy(), o["dclas"][i], what="dclas")
+            syn.assert_dreg_close(rd.grad[i:i + 1].cpu().numpy(), o["dreg"][i:i + 1])
+    except AssertionError:
+        ok_g = False
+    del cd, rd
+    return {"parity_checked": bool(ok_m and ok_n and rel3 <= 1e-5 and ok_g), "matches_equal": ok_m, "npos_equal": ok_n,
+            "loss_max_rel_err": rel3, "grads_rtol_1e-5": ok_g,
+            "what": "first timed batch (B=%d, A=%d, C=%d) vs the CPU oracle, outside the timed region" % (B, A, C)}
+
+
 def torch_cuda_baseline(cfg, device, n=4):
     """The reference's own sequence of torch operations (tests/torch_restatement.py, pinned bit for bit against the
     unmodified reference on CPU) executed with torch's CUDA kernels: what the reference does on a GPU, its intended
     mode.  The reference itself is Python and cannot travel to the GPU box.  images/s fwd+bwd."""
     import torch
 
-    from neuralnetworklibrary_b200 import testing as syn
+    from tests import synth as syn
     from neuralnetworklibrary_b200.retinanet import AnchorGenerator
     from tests import torch_restatement as tr
 
@@ -540,6 +659,12 @@ def run_ours(args):
     images = B * world * args.steps
     value = images / (total_ms * 1e-3)
     eager_ms, kern_ms, _ = time_loss_eager(anchors, sets, args.steps, args.warmup, device)
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        try:
+            parity = parity_check(anchors, sets[0], device)
+        except Exception as exc:
+            parity = {"parity_checked": False, "error": repr(exc)}
     del sets
 
     e2e_ms, h2d, d2h = time_loss_e2e(COCO, B, max(2, min(args.steps, 5)), args.warmup, device, world)
@@ -591,6 +716,9 @@ def run_ours(args):
                          "whole_step_frac": round(alg * args.steps / (total_ms * 1e-3) / 1e9 / peak, 4)},
             "clocks": clocks, "loss": last_loss,
         }
+        if parity is not None:
+            line["parity_checked"] = parity.pop("parity_checked")
+            line["parity"] = parity
         if b256 is not None:
             line["coco_b256_sharded"] = b256
         # extra workloads (device-timed, single GPU share of the job): post-processing and Pascal loss
@@ -664,8 +792,25 @@ def run_ours(args):
             except Exception as exc:
                 line["torch_cuda_baseline"] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
+            if reference_available():
+                try:
+                    rv, rsample = reference_cuda_loss(COCO, device)
+                    line["reference_cuda"] = {"value": round(rv, 1), "unit": "images/s", "kind": "reference", "sample": rsample}
+                except Exception as exc:
+                    line["reference_cuda"] = {"error": repr(exc)}
             v, cores, sample = cpu_baseline_loss(COCO)
-            line["cpu_baseline"] = {"value": round(v, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+            port = {"value": round(v, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+            line["cpu_baseline"] = port
+            if reference_available():
+                try:
+                    cv, cthreads, cdt, _ = reference_cpu_loss(COCO, 2, 6, 1)
+                    line["cpu_baseline"] = {"value": round(cv, 3), "unit": "images/s", "cores": cthreads, "kind": "reference",
+                                            "sample": "the unmodified reference (SSD_loss + backward, torch CPU kernels, %d intra-op "
+                                                      "threads): 6 passes over B=2 COCO-shaped images (800x1344, C=80, M=20), %.1f s"
+                                                      % (cthreads, cdt)}
+                    line["cpu_baseline_port"] = port
+                except Exception as exc:
+                    line["cpu_baseline_reference_error"] = repr(exc)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -674,46 +819,38 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm: the reference's algorithm on the host cores (oracle port; the reference is Python and
-# /root/reference does not exist on the GPU box)
+# reference arm: THE REFERENCE ITSELF on the host cores -- the unmodified sources staged in oracle/_ref (or the checkout
+# at /root/reference), SSD_loss + backward with torch's CPU kernels on all threads.  If the sources are not staged the arm
+# falls back to the C port of the algorithm (oracle/retina_oracle.c) and says so (`kind`).
 # --------------------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return None
-    import numpy as np
-
-    from neuralnetworklibrary_b200 import testing as syn
-    from oracle import oracle as orc
-
-    orc.build()
     H, W, C, M = COCO["H"], COCO["W"], COCO["C"], COCO["M"]
-    threads = orc.num_threads()
-    n = max(2, min(threads, 32))  # one step = a bounded sample: one COCO-shaped image per host thread
-    an = orc.anchors(H, W)
-    A = an.shape[0]
-    rng = np.random.default_rng(1002)
-    clas = (1.0 / (1.0 + np.exp(-(rng.standard_normal((n, A, C), dtype=np.float32) - np.float32(4.6))))).astype(np.float32)
-    reg = rng.standard_normal((n, A, 4), dtype=np.float32) * np.float32(0.5)
-    gb, gc = syn.make_targets(n, M, H, W, C, seed=1002)
-    gbn, gcn = gb.numpy(), gc.numpy()
-    for _ in range(min(args.warmup, 1)):
-        orc.loss(an, clas, reg, gbn, gcn)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.loss(an, clas, reg, gbn, gcn)
-    dt = time.perf_counter() - t0
-    value = n * args.steps / dt
-    sample = "%d COCO-shaped images (800x1344, A=%d, C=80, M=20) per step, 1 image per thread" % (n, A)
+    port_v, port_cores, port_sample = cpu_baseline_loss(COCO)
+    port = {"value": round(port_v, 3), "unit": "images/s", "cores": port_cores, "kind": "port", "sample": port_sample}
+    A = 201600
+    if reference_available():
+        n = 2   # one step = a bounded sample: B=2 COCO-shaped images (the reference is a per-image Python loop: linear in B)
+        value, threads, dt, _ = reference_cpu_loss(COCO, n, args.steps, min(args.warmup, 2))
+        kind = "reference"
+        sample = ("the unmodified reference (Applications/Vision.py SSD_loss + loss.backward()), torch CPU kernels with %d "
+                  "intra-op threads, %d COCO-shaped images (800x1344, A=%d, C=80, M=20) per step" % (threads, n, A))
+        cores = threads
+        ms_per_step = dt / args.steps * 1e3
+    else:
+        value, cores, sample, kind = port_v, port_cores, port_sample, "port"
+        ms_per_step = None
     line = {
         "impl": "reference", "metric": "images/sec loss fwd+bwd (COCO shape)", "value": round(value, 3), "unit": "images/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None if ms_per_step is None else round(ms_per_step, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "coco_loss_fwd_bwd: assign + focal/smooth-L1 fwd+bwd, 800x1344, A=%d, C=80, M=20" % A,
-                   "note": "reference algorithm on host cores (C port in oracle/; the reference itself is Python and is "
-                           "not present on the GPU box); bounded sample per step"},
-        "cpu_baseline": {"value": round(value, 3), "unit": "images/s", "cores": min(threads, n), "kind": "port", "sample": sample},
+                   "note": "the reference's own CPU implementation of the path on the host cores; bounded sample per step"},
+        "cpu_baseline": {"value": round(value, 3), "unit": "images/s", "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline_port": port,
         "e2e": {"value": round(value, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -731,6 +868,7 @@ def main():
     ap.add_argument("--postproc-batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-b256", action="store_true", help="skip the BASELINE configs[4] extra (256 images over the ranks)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle check of the first timed batch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -54,6 +54,14 @@ const char *rn_last_error(void);
 /* ABI version (bumped on any signature change). */
 int rn_abi_version(void);
 
+/* Process-wide tuning / test switches (all default 0; nothing is ever read from the environment).  Names:
+ *   "assign_dense" (!= 0: rn_assign always takes the dense kernel), "assign_no_balance", "assign_wbase" (dense kernel work
+ *   balancing), "loss_iters" (> 0: sub-tiles per CTA of rn_loss), "levels_nchunks" (> 0: class chunks per row tile of
+ *   rn_loss_levels), "step_unfused" (!= 0: rn_loss_step launches the separate assignment / loss / reduction kernels).
+ * rn_set_option returns RN_ERR_INVALID_ARG for an unknown name; rn_get_option returns -1 for one. */
+int rn_set_option(const char *name, int value);
+int rn_get_option(const char *name);
+
 /* A = K * sum_l ceil(H/2^l)*ceil(W/2^l), l = 3..7 (retinanet.py:488).  Host-only arithmetic. */
 int rn_num_anchors(int H, int W, int K);
 
@@ -67,8 +75,8 @@ int rn_anchors(int H, int W, const double *base /*host [5][K][4]*/, int K, float
  * max_iou ([B,A] fp32) may be NULL.
  * Two implementations with identical results: with generated anchors, max_iou == NULL, M <= 128 and
  * 0.2 <= neg_thr <= pos_thr a background fill plus one CTA per ground-truth box over that box's candidate anchors
- * (sparse); otherwise a dense walk over all anchors.  The environment variable RN_ASSIGN_DENSE forces the dense one
- * (used by the tests that compare the two). */
+ * (sparse); otherwise a dense walk over all anchors.  rn_set_option("assign_dense", 1) forces the dense one (used by
+ * the tests that compare the two). */
 int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, int M, int H, int W,
               const double *base /*host*/, int K, const float *anchors /*[A,4] or NULL*/, int A,
               float pos_thr, float neg_thr, int32_t *matches, int32_t *npos, float *max_iou, void *stream);

@@ -16,7 +16,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 # RETINA_B200_LIB overrides the library path (A/B comparisons of builds); the default is the in-tree build.
 LIB_PATH = os.environ.get("RETINA_B200_LIB") or os.path.join(_PKG, "libretina_sm100.so")
-SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_loss_tma.cu", "rn_post.cu", "rn_loss_levels.cu"]
+SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_post.cu", "rn_loss_levels.cu"]
 BUILD_DIR = os.path.join(_PKG, "csrc", "_build")   # object files (git-ignored); the .so is what travels
 
 NVCC_FLAGS = [
@@ -93,6 +93,8 @@ _pp = C.POINTER(C.c_void_p)   # host array of device pointers
 PROTOTYPES = {
     "rn_last_error": (C.c_char_p, []),
     "rn_abi_version": (C.c_int, []),
+    "rn_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "rn_get_option": (C.c_int, [C.c_char_p]),
     "rn_num_anchors": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "rn_anchors": (C.c_int, [C.c_int, C.c_int, _f64p, C.c_int, _f32p, _vp]),
     "rn_assign": (C.c_int, [_f32p, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _f32p, C.c_int,
@@ -156,6 +158,24 @@ def check(rc):
         if rc == RN_ERR_INVALID_ARG:
             raise ValueError(msg)  # the reference reports bad arguments as ValueError (Learner.py:339-340)
         raise RetinaB200Error("libretina_sm100 error %d: %s" % (rc, msg))
+
+
+class option(object):
+    """Context manager that sets a library tuning / test switch (rn_set_option) and restores it on exit, e.g.
+    `with _lib.option("assign_dense", 1): ...` forces the dense assignment kernel."""
+
+    def __init__(self, name, value):
+        self.name, self.value = name.encode(), int(value)
+
+    def __enter__(self):
+        lib = load()
+        self.old = lib.rn_get_option(self.name)
+        check(lib.rn_set_option(self.name, self.value))
+        return self
+
+    def __exit__(self, *exc):
+        check(load().rn_set_option(self.name, max(self.old, 0)))
+        return False
 
 
 def ptr(t):

@@ -23,7 +23,34 @@ int rn_check_launch(const char *what) {
 }
 
 extern "C" const char *rn_last_error(void) { return g_err; }
-extern "C" int rn_abi_version(void) { return 1; }
+extern "C" int rn_abi_version(void) { return 2; }
+
+// Process-wide tuning / test switches, set explicitly through the ABI (never read from the environment: a stray
+// variable in a training job must not change which kernel runs).  0 = default behaviour for every option.
+static const char *const g_opt_names[RN_OPT_COUNT] = {"assign_dense", "assign_no_balance", "assign_wbase", "loss_iters",
+                                                      "levels_nchunks", "step_unfused"};
+static int g_opt[RN_OPT_COUNT] = {0};
+
+int rn_opt(int id) { return (id >= 0 && id < RN_OPT_COUNT) ? g_opt[id] : 0; }
+
+static int rn_opt_index(const char *name) {
+    if (name)
+        for (int i = 0; i < RN_OPT_COUNT; ++i)
+            if (strcmp(name, g_opt_names[i]) == 0) return i;
+    return -1;
+}
+
+extern "C" int rn_set_option(const char *name, int value) {
+    const int i = rn_opt_index(name);
+    if (i < 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_set_option: unknown option '%s'", name ? name : "(null)");
+    g_opt[i] = value;
+    return RN_OK;
+}
+
+extern "C" int rn_get_option(const char *name) {
+    const int i = rn_opt_index(name);
+    return i < 0 ? -1 : g_opt[i];
+}
 
 extern "C" int rn_num_anchors(int H, int W, int K) {
     if (H <= 0 || W <= 0 || K <= 0) return 0;

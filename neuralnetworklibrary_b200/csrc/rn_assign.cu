@@ -9,8 +9,6 @@
 // Anchors are generated on the fly (float64 add -> float32, bit-identical to the reference) or read
 // from a caller-supplied table.  The IEEE divide only runs for overlapping pairs.  The work is compute
 // only (reads O(M) bytes per CTA, writes 4 B per anchor).
-#include <stdlib.h>
-
 #include "rn_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -343,7 +341,12 @@ rn_assign_sparse_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__re
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     rn_pdl_trigger();
     const int64_t *cats = gt_cats + (size_t)b * M;
-    if (cats[row] < 0) return;  // padding row (Vision.py:1637-1638); uniform over the CTA
+    if (cats[row] < 0) {  // padding row (Vision.py:1637-1638); uniform over the CTA
+        // Every CTA of a PDL-launched grid must wait: the grid's completion is what the loss kernel behind it waits for,
+        // and it only implies the completion of rn_assign_fill_kernel if no CTA retires without having waited for it.
+        rn_pdl_wait();
+        return;
+    }
     if (warp == 0) {            // compact the image's boxes (as rn_compact_gt) and find this CTA's box among them
         const float4 *boxes = gt_boxes + (size_t)b * M;
         int cnt = 0, self = 0;
@@ -593,7 +596,7 @@ extern "C" int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, i
     if (smem > 200 * 1024) return rn_set_error(RN_ERR_INVALID_ARG, "rn_assign: M=%d B=%d too large", M, B);
     cudaStream_t s = (cudaStream_t)stream;
     // Sparse path (see rn_assign_sparse_kernel): generated anchors, no max-IoU output, thresholds in the usual order.
-    if (!anchors && !max_iou && M >= 1 && M <= 128 && neg_thr >= 0.2f && pos_thr >= neg_thr && !getenv("RN_ASSIGN_DENSE")) {
+    if (!anchors && !max_iou && M >= 1 && M <= 128 && neg_thr >= 0.2f && pos_thr >= neg_thr && !rn_opt(RN_OPT_ASSIGN_DENSE)) {
         const size_t n = (size_t)B * (size_t)A;
         const int fill_ctas = 148 * 4;
         if (B <= fill_ctas * 256) {
@@ -621,8 +624,8 @@ extern "C" int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, i
     const long long nwt = ((long long)ncell * (k9 ? 3 : 1) + 31) / 32;
     const long long max_ctas = (nwt + nthr / 32 - 1) / (nthr / 32);  // per image
     int w_base = 11, w_box = 1;  // measured (COCO shape: 11.7 us without boxes + 1.04 us per box and image)
-    if (const char *e = getenv("RN_ASSIGN_WBASE")) w_base = atoi(e) > 0 ? atoi(e) : w_base;  // tuning overrides
-    const bool no_balance = getenv("RN_ASSIGN_NO_BALANCE") != nullptr;
+    if (rn_opt(RN_OPT_ASSIGN_WBASE) > 0) w_base = rn_opt(RN_OPT_ASSIGN_WBASE);  // tuning override (rn_set_option)
+    const bool no_balance = rn_opt(RN_OPT_ASSIGN_NO_BALANCE) != 0;
     const int total = RN_ASSIGN_CTAS * 148;
     dim3 grid;
     if (!no_balance && B > 1 && total >= 2 * B && (long long)total <= max_ctas * B && nwt >= 1024) {

@@ -34,6 +34,18 @@ int rn_set_error(int code, const char *fmt, ...);
 int rn_check_launch(const char *what);
 int rn_build_geom(RnGeom *g, int H, int W, const double *base, int K, const float *anchors, int A);
 
+// Tuning / test switches (rn_set_option; rn_abi.cu).  All default to 0.
+enum RnOption {
+    RN_OPT_ASSIGN_DENSE = 0,   // != 0: rn_assign always takes the dense kernel (tests compare it with the sparse path)
+    RN_OPT_ASSIGN_NO_BALANCE,  // != 0: dense kernel without the per-image work balancing
+    RN_OPT_ASSIGN_WBASE,       // > 0: base weight of an image in the dense kernel's balancing (default 11)
+    RN_OPT_LOSS_ITERS,         // > 0: sub-tiles per CTA of the flat loss kernel
+    RN_OPT_LVL_NCHUNKS,        // > 0: class chunks per row tile of the level-tensor loss
+    RN_OPT_STEP_UNFUSED,       // != 0: rn_loss_step runs the separate assignment / loss / reduction kernels
+    RN_OPT_COUNT
+};
+int rn_opt(int id);
+
 // ------------------------------------------------------------------------------------------------
 // Loads / stores
 // ------------------------------------------------------------------------------------------------

@@ -17,8 +17,6 @@
 // partial per CTA, then a one-CTA final kernel (one warp per image) that sums each image's partials in a
 // fixed order in float64 and combines the images in image order.  No floating-point atomics anywhere
 // => run-to-run bit-identical results.
-#include <stdlib.h>
-
 #include "rn_loss_math.cuh"
 
 #ifndef RN_LOSS_U
@@ -267,7 +265,7 @@ static int rn_loss_iters(int B, int A, int C) {
     const long long sub = ((long long)A * (C / V) + RN_LOSS_TILE - 1) / RN_LOSS_TILE;
     int it = 4;
     while (it > 1 && (long long)B * ((sub + it - 1) / it) < 4LL * 148 * 3) it >>= 1;
-    if (const char *e = getenv("RN_LOSS_ITERS")) it = atoi(e) > 0 ? atoi(e) : it;  // tuning override
+    if (rn_opt(RN_OPT_LOSS_ITERS) > 0) it = rn_opt(RN_OPT_LOSS_ITERS);  // tuning override (rn_set_option)
     return it;
 }
 static int rn_loss_tiles(int B, int A, int C) {  // CTAs (= partials) per image
@@ -367,9 +365,7 @@ static int rn_loss_impl(bool logits, float *probs, const float *clas, const floa
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(tiles, B);
     const bool g2 = (gamma == 2.0), grad = dclas != nullptr;
-    // experimental shared-memory staged variant (rn_loss_tma.cu), opt-in
-    if (V == 4 && getenv("RN_LOSS_TMA") && rn_launch_loss_tma(logits, g2, grad, grid, s, P, g)) {
-    } else if (logits) {
+    if (logits) {
         if (V == 4 && C == 80) rn_launch_loss<4, 20, true>(g2, grad, grid, smem, s, P, g);
         else if (V == 4 && C == 20) rn_launch_loss<4, 5, true>(g2, grad, grid, smem, s, P, g);
         else if (V == 4) rn_launch_loss<4, 0, true>(g2, grad, grid, smem, s, P, g);

@@ -440,7 +440,7 @@ static void rn_lvl_plan(RnLvlPlan *pl, int B, int H, int W, int K, int C, bool l
     const int blocks = (C + RN_LVL_CHUNK_Q - 1) / RN_LVL_CHUNK_Q;
     int nch = 1;
     while (nch < blocks && (long long)B * pl->tile0[RN_NUM_LEVELS] * nch < 8LL * 148 * ctas) ++nch;
-    if (const char *e = getenv("RN_LVL_NCHUNKS")) nch = max(1, min(blocks, atoi(e)));  // tuning override
+    if (rn_opt(RN_OPT_LVL_NCHUNKS) > 0) nch = max(1, min(blocks, rn_opt(RN_OPT_LVL_NCHUNKS)));  // tuning override (rn_set_option)
     int cchunk = ((blocks + nch - 1) / nch) * RN_LVL_CHUNK_Q;
     if (cchunk > C) cchunk = C;
     pl->cchunk = cchunk;

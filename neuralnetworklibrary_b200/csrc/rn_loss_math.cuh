@@ -205,53 +205,6 @@ struct RnVec<1> {
 };
 
 
-// One 128-bit vector of class activations of anchor row v / CV (m = that row's assignment): element math as in
-// rn_loss_subtile (rn_loss.cu), used by the shared-memory staged kernel (rn_loss_tma.cu).  Returns the gradient vector.
-template <int CVT, bool G2, bool GRAD, bool LOGITS>
-__device__ __forceinline__ float4 rn_loss_vector4(const RnLossParams &P, float4 x, int m, int v, int CV, const int *s_cat,
-                                                  float gl, float *probs_vec, float &acc_neg, float &acc_pos) {
-    const float a_row = (m == RN_MATCH_IGNORE) ? 0.0f : P.a_neg;  // ignored anchors contribute nothing
-    const float ga = a_row * gl;
-    float part = 0.0f;
-    float y[4] = {x.x, x.y, x.z, x.w}, gq[4];
-    if (LOGITS) {
-        rn_sigmoid_pair(x.x, x.y, y[0], y[1]);
-        rn_sigmoid_pair(x.z, x.w, y[2], y[3]);
-    }
-    bool slow = false;
-    int pe = -1;
-    if (m >= 0) {  // rare: a positive anchor; is its class inside this vector?  (Vision.py:1588-1593)
-        pe = s_cat[m] - (v - (v / CV) * CV) * 4;
-        slow = (unsigned)pe < 4u;
-    }
-    if (!slow && G2) {
-        rn_f2 acc2 = 0ull;
-        const rn_f2 ga2 = rn_splat(ga);
-        rn_focal_pair_neg<GRAD, LOGITS>(y[0], y[1], P.lo, P.hi, ga2, acc2, gq[0], gq[1]);
-        rn_focal_pair_neg<GRAD, LOGITS>(y[2], y[3], P.lo, P.hi, ga2, acc2, gq[2], gq[3]);
-        float s0, s1;
-        rn_unpack(acc2, s0, s1);
-        part = s0 + s1;
-    } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (e == pe) {
-                float pp = 0.0f;
-                gq[e] = rn_focal_elem<true, G2, GRAD>(y[e], P.lo, P.hi, P.gamma, P.a_pos * gl, pp);
-                acc_pos = fmaf(0.5f * P.a_pos, pp, acc_pos);
-            } else {
-                gq[e] = rn_focal_elem<false, G2, GRAD>(y[e], P.lo, P.hi, P.gamma, ga, part);
-            }
-            if (LOGITS && GRAD) gq[e] = (gq[e] * (1.0f - y[e])) * y[e];  // sigmoid backward
-        }
-    }
-    if (LOGITS && probs_vec) *reinterpret_cast<float4 *>(probs_vec) = make_float4(y[0], y[1], y[2], y[3]);
-    acc_neg = fmaf(0.5f * a_row, part, acc_neg);
-    return make_float4(gq[0], gq[1], gq[2], gq[3]);
-}
-
-bool rn_launch_loss_tma(bool logits, bool g2, bool grad, dim3 grid, cudaStream_t s, const RnLossParams &P, const RnGeom &g);
-
 // One CTA, one warp per image: sums the image's CTA partials in a fixed order (float64), normalises like
 // the reference (Vision.py:1530, :1566); thread 0 then accumulates over images in fp32 in image order
 // (Vision.py:1640-1641) and combines (Vision.py:1643-1644).  (Folding this into the loss kernel

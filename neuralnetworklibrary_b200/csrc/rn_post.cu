@@ -692,16 +692,21 @@ static int rn_launch_select_nms(bool from_boxes, int B, int cap, RnNmsParams &P,
     P.cand_counts = reinterpret_cast<const int32_t *>(ws + L.counts);
     const size_t smem = sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4 +
                         (size_t)P.top_k * (sizeof(float4) + sizeof(float) + 2 * sizeof(int));
-    cudaError_t e;
-    if (from_boxes) {
-        e = cudaFuncSetAttribute(rn_post_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_nms smem: %s", cudaGetErrorString(e));
-        rn_launch_pdl(rn_post_nms_kernel<true>, dim3(B), dim3(RN_SEL_THREADS), smem, s, P, g, dec);
-    } else {
-        e = cudaFuncSetAttribute(rn_post_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_postproc smem: %s", cudaGetErrorString(e));
-        rn_launch_pdl(rn_post_nms_kernel<false>, dim3(B), dim3(RN_SEL_THREADS), smem, s, P, g, dec);
+    // the opt-in for > 48 KB of dynamic shared memory is made once per process (and device), for the largest top_k
+    static bool s_attr_done[2][64] = {};
+    int devi = 0;
+    cudaGetDevice(&devi);
+    if (devi >= 0 && devi < 64 && !s_attr_done[from_boxes ? 1 : 0][devi]) {
+        const int max_smem = (int)(sizeof(double) * RN_NUM_LEVELS * RN_MAX_K * 4 +
+                                   (size_t)RN_MAX_TOP_K * (sizeof(float4) + sizeof(float) + 2 * sizeof(int)));
+        cudaError_t e = from_boxes
+            ? cudaFuncSetAttribute(rn_post_nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
+            : cudaFuncSetAttribute(rn_post_nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_post_nms smem: %s", cudaGetErrorString(e));
+        s_attr_done[from_boxes ? 1 : 0][devi] = true;
     }
+    if (from_boxes) rn_launch_pdl(rn_post_nms_kernel<true>, dim3(B), dim3(RN_SEL_THREADS), smem, s, P, g, dec);
+    else rn_launch_pdl(rn_post_nms_kernel<false>, dim3(B), dim3(RN_SEL_THREADS), smem, s, P, g, dec);
     return rn_check_launch("rn_post_nms");
 }
 

@@ -1,6 +1,6 @@
 import sys, os, torch
 sys.path.insert(0, os.getcwd())
-from neuralnetworklibrary_b200 import testing as syn
+from tests import synth as syn
 from neuralnetworklibrary_b200.retinanet import AnchorGenerator
 from neuralnetworklibrary_b200.vision import assign_batch
 dev = torch.device("cuda:0")

@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from neuralnetworklibrary_b200 import testing as syn  # noqa: E402
+from tests import synth as syn  # noqa: E402
 from neuralnetworklibrary_b200.retinanet import AnchorGenerator  # noqa: E402
 from neuralnetworklibrary_b200.vision import assign_batch  # noqa: E402
 

@@ -1,7 +1,7 @@
 import sys, os, torch, json
 sys.path.insert(0, os.getcwd())
 import bench
-from neuralnetworklibrary_b200 import testing as syn
+from tests import synth as syn
 from neuralnetworklibrary_b200.retinanet import AnchorGenerator
 from neuralnetworklibrary_b200.vision import SSD_loss, level_shapes, _launch_loss_levels, _launch_loss
 dev = torch.device("cuda:0")

@@ -1,4 +1,4 @@
-"""Multi-GPU functional check (not a pytest module: launch with torchrun on a box with >= 2 GPUs):
+"""Multi-GPU functional check (launched by tests/test_gpu_distributed.py, or by hand with torchrun on a box with >= 2 GPUs):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29520 tests/dist_gpu_check.py
 
@@ -16,7 +16,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from neuralnetworklibrary_b200 import distributed as nd  # noqa: E402
-from neuralnetworklibrary_b200 import testing as syn  # noqa: E402
+from tests import synth as syn  # noqa: E402
 from neuralnetworklibrary_b200.retinanet import AnchorGenerator, BBoxPredictor  # noqa: E402
 from neuralnetworklibrary_b200.vision import SSD_loss  # noqa: E402
 from oracle import oracle as orc  # noqa: E402

@@ -2,7 +2,7 @@
 
 Run in the build container only (needs /root/reference):  python tests/golden/make_golden.py
 The reference is imported through oracle/ref_shim.py (CPU torch, `Tensor.cuda` no-op) and executed on
-seeded synthetic inputs (neuralnetworklibrary_b200/testing.py).  Inputs that
+seeded synthetic inputs (tests/synth.py).  Inputs that
 are cheap to store are stored next to the outputs, larger ones are re-generated from their seed and
 pinned by a SHA-256 of their bytes.
 """
@@ -16,7 +16,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from neuralnetworklibrary_b200 import testing as syn  # noqa: E402
+from tests import synth as syn  # noqa: E402
 from tests import ref_runner as ref  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))

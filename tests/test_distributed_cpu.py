@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from neuralnetworklibrary_b200 import distributed as nd
-from neuralnetworklibrary_b200 import testing as syn
+from tests import synth as syn
 
 
 def test_shard_bounds_cover_and_balance():

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from neuralnetworklibrary_b200 import testing as syn
+from tests import synth as syn
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -305,31 +305,3 @@ def test_loss_from_logits(seed, H, W, C, B, M, kw):
     with torch.no_grad():
         l2 = f2([anchors, reg.to(dev()), f.last_probs], [gb.to(dev()), gc.to(dev())])
     assert l2.item() == loss.item()
-
-
-@pytest.mark.parametrize("seed,H,W,C,B,M,logits", [(401, 128, 160, 80, 2, 6, False), (402, 100, 167, 20, 3, 5, False), (403, 96, 128, 12, 2, 4, True)])
-def test_loss_tma_staged_variant(seed, H, W, C, B, M, logits):
-    """The experimental shared-memory staged kernel (rn_loss_tma.cu: cp.async.bulk + mbarrier, opt-in via RN_LOSS_TMA)
-    computes exactly what the default kernel computes: same loss bits, same gradients."""
-    from neuralnetworklibrary_b200.vision import SSD_loss
-    anchors, an = make_anchors(H, W), orc.anchors(H, W)
-    gb, gc = syn.make_targets(B, M, H, W, C, seed=seed, min_side=10.0, max_frac=0.7)
-    clas, reg = syn.make_train_activations(B, an.shape[0], C, seed=seed, edge_cases=64)
-    if logits:
-        clas = torch.logit(clas.clamp(1e-6, 1 - 1e-6))
-    out = []
-    for tma in (False, True):
-        if tma:
-            os.environ["RN_LOSS_TMA"] = "1"
-        try:
-            cd, rd = clas.to(dev()).requires_grad_(True), reg.to(dev()).requires_grad_(True)
-            f = SSD_loss(from_logits=logits)
-            loss = f([anchors, rd, cd], [gb.to(dev()), gc.to(dev())])
-            loss.backward()
-            torch.cuda.synchronize()
-            out.append((loss.item(), f.reg_loss.item(), f.clas_loss.item(), cd.grad.clone(), rd.grad.clone()))
-        finally:
-            os.environ.pop("RN_LOSS_TMA", None)
-    a, b = out
-    np.testing.assert_allclose(np.array(a[:3]), np.array(b[:3]), rtol=1e-6)
-    assert torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])

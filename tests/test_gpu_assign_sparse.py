@@ -1,9 +1,7 @@
 """The sparse assignment path of rn_assign (one CTA per ground-truth box enumerating that box's candidate anchors) against
-the dense kernel of the same library (RN_ASSIGN_DENSE=1) and against the CPU oracle: matches and positive counts must be
+the dense kernel of the same library (rn_set_option("assign_dense", 1)) and against the CPU oracle: matches and positive counts must be
 identical for every box geometry -- tiny, huge, partly or completely outside the image, degenerate, duplicated, touching
 the thresholds' neighbourhood -- because a box whose window missed a single anchor would silently turn it into background."""
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -18,14 +16,11 @@ def dev():
 
 
 def _assign(anchors, gb, gc, dense, **kw):
+    from neuralnetworklibrary_b200 import _lib
     from neuralnetworklibrary_b200.vision import assign_batch
-    if dense:
-        os.environ["RN_ASSIGN_DENSE"] = "1"
-    try:
+    with _lib.option("assign_dense", 1 if dense else 0):
         m, n, _ = assign_batch(anchors, gb, gc, **kw)
         torch.cuda.synchronize()
-    finally:
-        os.environ.pop("RN_ASSIGN_DENSE", None)
     return m.cpu().numpy(), n.cpu().numpy()
 
 

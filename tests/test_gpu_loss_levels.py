@@ -3,12 +3,12 @@ NCHW conv outputs per pyramid level instead of the permuted + concatenated [bs, 
 CPU oracle on the flat tensors, with the layout map of retinanet.py:215-217, :289-295 / Vision.py:1467-1468 restated
 in oracle.heads_to_flat (pinned against the unmodified reference heads in tests/test_oracle_vs_reference.py).
 Assignments bit-exact; loss and gradients rtol 1e-5 with identical zero patterns (dreg: the scaled tolerance of
-neuralnetworklibrary_b200/testing.py)."""
+tests/synth.py)."""
 import numpy as np
 import pytest
 import torch
 
-from neuralnetworklibrary_b200 import testing as syn
+from tests import synth as syn
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from neuralnetworklibrary_b200 import testing as syn
+from tests import synth as syn
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from neuralnetworklibrary_b200 import testing as syn
+from tests import synth as syn
 from oracle import oracle as orc
 
 RTOL = 1e-5

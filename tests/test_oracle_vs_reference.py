@@ -3,7 +3,7 @@ checkout exists (the build container); the committed golden fixtures cover every
 import numpy as np
 import pytest
 
-from neuralnetworklibrary_b200 import testing as syn
+from tests import synth as syn
 from oracle import oracle as orc
 from tests import ref_runner as ref
 from tests.test_oracle_golden import assert_rel

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from neuralnetworklibrary_b200 import testing as syn
+from tests import synth as syn
 from oracle import oracle as orc
 from tests import ref_runner as ref
 from tests import torch_restatement as tr
@@ -103,7 +103,9 @@ def test_kernels_vs_restatement_on_cuda_loss(seed, H, W, C, B, M, kw):
     got3 = np.array([loss.item(), f.reg_loss.item(), f.clas_loss.item()], np.float32)
     np.testing.assert_allclose(got3, out3, rtol=RTOL, atol=0)
     syn.assert_rel(cd.grad.cpu().numpy(), dclas, what="dclas")
-    syn.assert_dreg_close(rd.grad.cpu().numpy(), dreg)
+    # both sides evaluate logf with the device libm here, so the scaled tolerance that the host-libm C oracle needs does
+    # not apply: PURE rtol 1e-5, atol 0, identical zero pattern
+    syn.assert_rel(rd.grad.cpu().numpy(), dreg, what="dreg")
 
 
 @pytest.mark.gpu
