@@ -228,9 +228,9 @@ def test_loss_sharded_partials_add_up():
     assert np.array_equal(np.concatenate([g[1] for g in grads]), full[2])
 
 
-@pytest.mark.parametrize("H,W,C,B,M,seed", [(800, 1344, 80, 2, 20, 1002), (512, 512, 20, 4, 10, 1003)])
+@pytest.mark.parametrize("H,W,C,B,M,seed", [(800, 1344, 80, 2, 20, 1002), (512, 512, 20, 4, 10, 1003), (800, 1333, 80, 2, 20, 1006)])
 def test_loss_full_size(H, W, C, B, M, seed):
-    """BASELINE.json shapes (COCO 800x1344 / Pascal 512x512) at a batch the oracle finishes in seconds."""
+    """BASELINE.json shapes (COCO 800x1344 and, as named, 800x1333 = 200 700 anchors / Pascal 512x512) at a batch the oracle finishes in seconds."""
     anchors = make_anchors(H, W)
     an = orc.anchors(H, W)
     gb, gc = syn.make_targets(B, M, H, W, C, seed=seed)

@@ -47,6 +47,7 @@ def _setup(seed, H, W, C, B, M, logits=False):
     (304, 96, 160, 7, 3, 4, {}),
     (305, 64, 96, 12, 2, 4, dict(gamma=1.5)),
     (306, 256, 256, 91, 1, 10, {}),
+    (307, 800, 1333, 80, 1, 20, {}),     # COCO as named (A = 200 700): grid widths 167/84/42/21/11 -> the V=1 and V=2 plane paths at full size
 ])
 def test_levels_loss_matches_oracle(seed, H, W, C, B, M, kw):
     from neuralnetworklibrary_b200.vision import SSD_loss
@@ -69,7 +70,8 @@ def test_levels_loss_matches_oracle(seed, H, W, C, B, M, kw):
     np.testing.assert_allclose(l_flat.item(), loss.item(), rtol=RTOL)
 
 
-@pytest.mark.parametrize("seed,H,W,C,B,M", [(311, 128, 160, 80, 2, 6), (312, 100, 167, 20, 2, 5), (313, 96, 96, 7, 2, 4)])
+@pytest.mark.parametrize("seed,H,W,C,B,M", [(311, 128, 160, 80, 2, 6), (312, 100, 167, 20, 2, 5), (313, 96, 96, 7, 2, 4),
+                                                 (314, 800, 1333, 80, 1, 20)])
 def test_levels_loss_from_logits(seed, H, W, C, B, M):
     """Sigmoid fused (as rn_loss_logits): the oracle is fed the kernel's own probabilities, see
     tests/test_gpu_assign_loss.py::test_loss_from_logits for why."""
@@ -159,7 +161,8 @@ def test_levels_all_images_empty_and_other_anchor_sets():
 
 
 @pytest.mark.parametrize("seed,H,W,C,B,mu,kw", [(341, 128, 160, 12, 2, -5.0, {}), (342, 100, 167, 80, 2, -5.5, dict(thresh=0.1, max_overlap=0.4, top_k=300, max_boxes=50)),
-                                                (343, 256, 320, 20, 3, -5.0, dict(top_k=64, max_boxes=64)), (344, 800, 1344, 80, 1, -6.0, {})])
+                                                (343, 256, 320, 20, 3, -5.0, dict(top_k=64, max_boxes=64)), (344, 800, 1344, 80, 1, -6.0, {}),
+                                                (345, 800, 1333, 80, 1, -6.0, {})])
 def test_predictor_on_level_tensors(seed, H, W, C, B, mu, kw):
     """rn_postproc_levels (BBoxPredictor called with the heads' per-level NCHW tensors) against the flat path of this
     library and the oracle: candidate counts, keep indices, classes, scores and boxes identical.  With logits in, the

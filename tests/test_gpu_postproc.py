@@ -143,7 +143,7 @@ def test_nms_empty_and_single():
     assert len(nms(bx, torch.tensor([1, 1]), torch.tensor([0.9, 0.8]), max_overlap=0.5)[0]) == 2
 
 
-@pytest.mark.parametrize("H,W,C,B,seed", [(800, 1344, 80, 2, 1004)])
+@pytest.mark.parametrize("H,W,C,B,seed", [(800, 1344, 80, 2, 1004), (800, 1333, 80, 2, 1007)])
 def test_postproc_full_size(H, W, C, B, seed):
     """BASELINE.json COCO post-processing shape (A = 201600, 80 classes) at a batch the oracle finishes
     in seconds, plus size-independent properties of the result."""
