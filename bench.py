@@ -576,7 +576,7 @@ def parity_check(anchors, cap_set, device):
     B, A, C = clas.shape
     H, W = anchors._rn_geom.H, anchors._rn_geom.W
     cd, rd = clas.detach().clone().requires_grad_(True), reg.detach().clone().requires_grad_(True)
-    f = SSD_loss()
+    f = SSD_loss(keep_matches=True)   # the fused step also writes its dense assignment for this check
     loss = f([anchors, rd, cd], [gb, gc])
     loss.backward()
     matches, npos = f.last_assignment

@@ -121,6 +121,24 @@ int rn_loss(const float *clas, const float *reg, const float *gt_boxes, const in
             double gamma, double beta, int B_global, float *dclas, float *dreg, float *out3,
             void *workspace, size_t workspace_bytes, void *stream);
 
+/* The whole training step in ONE launch: rn_assign + rn_loss (or rn_loss_logits when from_logits != 0) + the final
+ * reduction, i.e. SSD_loss.__call__ with its assignment (Vision.py:1474-1511, :1568-1644) and the autograd replay
+ * (General/Learner.py:514).  Same inputs, outputs and numerics as the two separate calls; pos_thr / neg_thr are the
+ * thresholds of match_anchors_objects (0.5 / 0.4).  npos_out [B] (positives per image) and matches_out [B,A] (the
+ * rn_assign encoding; costs 4*A*B bytes of stores, meant for inspection and tests) may be NULL.
+ * With generated anchors (anchors == NULL), 1 <= M <= 128 and 0.2 <= neg_thr <= pos_thr the step is a single persistent
+ * kernel (rn_step.cu): one warp per ground-truth box writes a byte per non-background anchor, the CTAs stream equal slices
+ * of the B*A rows and the last CTA reduces; otherwise (or after rn_set_option("step_unfused", 1)) the separate kernels run.
+ * The workspace (rn_loss_step_workspace_bytes, 256-byte aligned) must be ZERO-INITIALISED once before its first use
+ * (rn_loss_step_workspace_init, or any memset) and every call leaves it zeroed again; one workspace per stream. */
+size_t rn_loss_step_workspace_bytes(int B, int A, int C);
+int rn_loss_step_workspace_init(void *workspace, size_t workspace_bytes, void *stream);
+int rn_loss_step(const float *clas, const float *reg, const float *gt_boxes, const int64_t *gt_cats, int B, int A,
+                 int C, int M, int H, int W, const double *base /*host*/, int K, const float *anchors /*or NULL*/,
+                 float pos_thr, float neg_thr, double alpha, double gamma, double beta, int B_global, int from_logits,
+                 float *dclas, float *dreg, float *probs_out, float *out3, int32_t *npos_out, int32_t *matches_out,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
 /* Same as rn_loss, but the class activations are LOGITS: the head's nn.Sigmoid (retinanet.py:258, :286) is
  * fused into the kernel (y = 1/(1+exp(-z)) within ~5 ulp of the correctly rounded value) and
  * dlogits = d loss / d logits (chained through sigmoid's backward, grad*(1-y)*y).  SURVEY.md section 8f row 1:

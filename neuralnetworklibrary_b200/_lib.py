@@ -16,7 +16,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 # RETINA_B200_LIB overrides the library path (A/B comparisons of builds); the default is the in-tree build.
 LIB_PATH = os.environ.get("RETINA_B200_LIB") or os.path.join(_PKG, "libretina_sm100.so")
-SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_post.cu", "rn_loss_levels.cu"]
+SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_step.cu", "rn_post.cu", "rn_loss_levels.cu"]
 BUILD_DIR = os.path.join(_PKG, "csrc", "_build")   # object files (git-ignored); the .so is what travels
 
 NVCC_FLAGS = [
@@ -110,6 +110,11 @@ PROTOTYPES = {
     "rn_loss_logits": (C.c_int, [_f32p, _f32p, _f32p, _i64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, _f64p, C.c_int, _f32p, C.c_double, C.c_double, C.c_double, C.c_int,
                                  _f32p, _f32p, _f32p, _f32p, _vp, C.c_size_t, _vp]),
+    "rn_loss_step_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "rn_loss_step_workspace_init": (C.c_int, [_vp, C.c_size_t, _vp]),
+    "rn_loss_step": (C.c_int, [_f32p, _f32p, _f32p, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int,
+                               _f32p, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                               _f32p, _f32p, _f32p, _f32p, _i32p, _i32p, _vp, C.c_size_t, _vp]),
     "rn_scale_grads": (C.c_int, [_f32p, C.c_size_t, _f32p, C.c_size_t, _f32p, _vp]),
     "rn_postproc_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rn_postproc": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _f32p,
@@ -211,15 +216,18 @@ def base_ptr(base_np):
 
 class Workspace(object):
     """Grow-only per-(device, stream) scratch buffer handed to the library (256-byte aligned by the
-    caching allocator)."""
+    caching allocator).  zeroed=True: the buffer is zero-filled when it is (re)allocated -- the contract of
+    rn_loss_step, whose kernel leaves its workspace zeroed again after every call."""
 
-    def __init__(self):
+    def __init__(self, zeroed=False):
         self._bufs = {}
+        self._zeroed = zeroed
 
     def get(self, nbytes, device):
         key = (device.index, torch.cuda.current_stream(device).cuda_stream)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            alloc = torch.zeros if self._zeroed else torch.empty
+            buf = alloc(max(int(nbytes), 256), dtype=torch.uint8, device=device)
             self._bufs[key] = buf
         return buf

@@ -205,6 +205,152 @@ struct RnVec<1> {
 };
 
 
+
+// How the assignment of an anchor row reaches the loss kernels; load() returns the canonical value (>= 0 index of the
+// matched ground-truth box, RN_MATCH_NEG, RN_MATCH_IGNORE).
+struct RnMatchI32 {  // matches [B,A] int32 written by rn_assign
+    typedef int32_t T;
+    static __device__ __forceinline__ int load(const int32_t *p, int i) { return __ldg(p + i); }
+};
+struct RnMatchU8 {  // byte codes of the fused step: 0 background, 255 ignored, 1 + index otherwise
+    typedef uint8_t T;
+    static __device__ __forceinline__ int load(const uint8_t *p, int i) {
+        // a plain (coherent) load: the bytes were written by other CTAs of the SAME grid, see rn_step.cu
+        unsigned c;
+        asm volatile("ld.global.u8 %0, [%1];" : "=r"(c) : "l"(p + i));
+        return c == 0u ? RN_MATCH_NEG : (c == 255u ? RN_MATCH_IGNORE : (int)c - 1);
+    }
+};
+
+// Smooth-L1 of one positive anchor (Vision.py:1532-1566): anchor `an`, its ground-truth box `tg`, predicted offsets `pr`.
+// ge = (1-beta) / (B * 4 * npos): the mean() backward.  Adds the four loss terms to acc_reg, returns d loss / d reg.
+__device__ __forceinline__ float4 rn_smooth_l1_row(float4 an, float4 tg, float4 pr, float ge, float &acc_reg) {
+    const float knee = (float)(1.0 / 9.0), off = (float)(0.5 / 9.0);  // Vision.py:1565
+    const float aw = __fsub_rn(an.z, an.x), ah = __fsub_rn(an.w, an.y);
+    const float acx = __fadd_rn(an.x, __fmul_rn(0.5f, aw)), acy = __fadd_rn(an.y, __fmul_rn(0.5f, ah));
+    float tw = __fsub_rn(tg.z, tg.x), th = __fsub_rn(tg.w, tg.y);
+    const float tcx = __fadd_rn(tg.x, __fmul_rn(0.5f, tw)), tcy = __fadd_rn(tg.y, __fmul_rn(0.5f, th));
+    tw = fmaxf(tw, 1.0f);  // Vision.py:1553-1554
+    th = fmaxf(th, 1.0f);
+    float ts[4], pv[4] = {pr.x, pr.y, pr.z, pr.w}, gg[4];
+    ts[0] = __fdiv_rn(__fdiv_rn(__fsub_rn(tcx, acx), aw), 0.1f);  // Vision.py:1556, :1562
+    ts[1] = __fdiv_rn(__fdiv_rn(__fsub_rn(tcy, acy), ah), 0.1f);
+    ts[2] = __fdiv_rn(logf(__fdiv_rn(tw, aw)), 0.2f);             // Vision.py:1558
+    ts[3] = __fdiv_rn(logf(__fdiv_rn(th, ah)), 0.2f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float d = __fsub_rn(ts[k], pv[k]);
+        const float diff = fabsf(d);
+        float l, gd;
+        if (diff < knee) {
+            l = __fmul_rn(4.5f, __fmul_rn(diff, diff));
+            gd = __fmul_rn(__fmul_rn(ge, 4.5f), __fmul_rn(2.0f, diff));
+        } else {
+            l = __fsub_rn(diff, off);
+            gd = ge;
+        }
+        acc_reg += l;
+        gg[k] = d > 0.0f ? -gd : (d < 0.0f ? gd : 0.0f);  // -sign(t - p) * gd
+    }
+    return make_float4(gg[0], gg[1], gg[2], gg[3]);
+}
+
+#ifndef RN_LOSS_U
+#define RN_LOSS_U 8  // vectors per thread
+#endif
+#define RN_LOSS_TILE (RN_THREADS * RN_LOSS_U)
+
+
+// One sub-tile of RN_LOSS_TILE vectors: U independent 128-bit loads per thread are issued first, then
+// the element math, then the stores.  FULL = the sub-tile lies completely inside the image, so there is
+// no per-vector bounds predicate; addresses are one 64-bit base per thread plus immediates.
+// MT: how the assignment of a row is stored (RnMatchI32: the int32 matches of rn_assign; RnMatchU8: the byte codes of the
+// fused step, rn_step.cu).  b = image (for probs_out), nvec = vectors per image, vend = end of the range this call may touch.
+template <int V, int CVT, bool G2, bool GRAD, bool FULL, bool LOGITS, typename MT>
+__device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, int b, const float *__restrict__ x_img,
+                                                float *__restrict__ dx_img, const typename MT::T *__restrict__ m_img,
+                                                const int *s_cat, int CV, int nvec, int vend, int tile0, float gl,
+                                                float &acc_neg, float &acc_pos) {
+    const int tid = threadIdx.x;
+    const int v0 = tile0 + tid;
+    const float *xp = x_img + (size_t)v0 * V;
+    RnVec<V> xv[RN_LOSS_U];
+    int mrow[RN_LOSS_U];
+#pragma unroll
+    for (int u = 0; u < RN_LOSS_U; ++u) {
+        const int v = v0 + u * RN_THREADS;
+        if (FULL || v < vend) {
+            xv[u].load(xp + (size_t)u * RN_THREADS * V);
+            mrow[u] = MT::load(m_img, v / CV);
+        } else {
+            mrow[u] = RN_MATCH_IGNORE;
+#pragma unroll
+            for (int e = 0; e < V; ++e) xv[u].at(e) = 0.5f;
+        }
+    }
+    float *dp = GRAD ? dx_img + (size_t)v0 * V : nullptr;
+#pragma unroll
+    for (int u = 0; u < RN_LOSS_U; ++u) {
+        const int m = mrow[u];
+        const float a_row = (m == RN_MATCH_IGNORE) ? 0.0f : P.a_neg;  // ignored anchors contribute nothing
+        const float ga = a_row * gl;
+        float part = 0.0f;
+        RnVec<V> gv;
+        float y[V];  // probabilities: the input itself, or sigmoid(logit)
+        if (LOGITS && V == 4) {
+            rn_sigmoid_pair(xv[u].at(0), xv[u].at(1), y[0], y[1]);
+            rn_sigmoid_pair(xv[u].at(2), xv[u].at(3), y[2 % V], y[3 % V]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e) y[e] = LOGITS ? rn_sigmoid(xv[u].at(e)) : xv[u].at(e);
+        }
+        bool slow = false;
+        int pe = -1;
+        if (m >= 0) {  // rare: a positive anchor; is its class inside this vector?  (Vision.py:1588-1593)
+            const int v = v0 + u * RN_THREADS;
+            pe = s_cat[m] - (v - (v / CV) * CV) * V;
+            slow = (unsigned)pe < (unsigned)V;
+        }
+        if (!slow) {  // common case: every element has target 0
+            if (V == 4 && G2) {
+                rn_f2 acc2 = 0ull;  // (+0.0f, +0.0f)
+                const rn_f2 ga2 = rn_splat(ga);
+                rn_focal_pair_neg<GRAD, LOGITS>(y[0], y[1], P.lo, P.hi, ga2, acc2, gv.at(0), gv.at(1));
+                rn_focal_pair_neg<GRAD, LOGITS>(y[2], y[3], P.lo, P.hi, ga2, acc2, gv.at(2), gv.at(3));
+                float s0, s1;
+                rn_unpack(acc2, s0, s1);
+                part = s0 + s1;
+            } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) gv.at(e) = rn_focal_elem<false, G2, GRAD>(y[e], P.lo, P.hi, P.gamma, ga, part);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                if (e == pe) {
+                    float pp = 0.0f;
+                    gv.at(e) = rn_focal_elem<true, G2, GRAD>(y[e], P.lo, P.hi, P.gamma, P.a_pos * gl, pp);
+                    acc_pos = fmaf(0.5f * P.a_pos, pp, acc_pos);
+                } else {
+                    gv.at(e) = rn_focal_elem<false, G2, GRAD>(y[e], P.lo, P.hi, P.gamma, ga, part);
+                }
+            }
+        }
+        if (LOGITS && P.probs != nullptr && (FULL || v0 + u * RN_THREADS < vend)) {
+            float *pp = P.probs + ((size_t)b * nvec + v0 + (size_t)u * RN_THREADS) * V;
+#pragma unroll
+            for (int e = 0; e < V; ++e) pp[e] = y[e];
+        }
+        if (LOGITS && GRAD && !(V == 4 && G2 && !slow)) {  // sigmoid backward: grad * (1 - y) * y (the packed path chains itself)
+#pragma unroll
+            for (int e = 0; e < V; ++e) gv.at(e) = (gv.at(e) * (1.0f - y[e])) * y[e];
+        }
+        acc_neg = fmaf(0.5f * a_row, part, acc_neg);
+        if (GRAD && (FULL || v0 + u * RN_THREADS < vend)) gv.store(dp + (size_t)u * RN_THREADS * V);
+    }
+}
+
+
 // One CTA, one warp per image: sums the image's CTA partials in a fixed order (float64), normalises like
 // the reference (Vision.py:1530, :1566); thread 0 then accumulates over images in fp32 in image order
 // (Vision.py:1640-1641) and combines (Vision.py:1643-1644).  (Folding this into the loss kernel

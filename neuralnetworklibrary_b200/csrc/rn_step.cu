@@ -1,0 +1,617 @@
+// rn_step.cu -- the whole training step of the path (anchor/GT assignment + focal/smooth-L1 loss forward AND backward +
+// the final reduction) in ONE persistent kernel launch.
+//
+// Replaces (reference file:line): match_anchors_objects Vision.py:1474-1511 (+ jaccard :234-256, the padding strip
+// :1637-1638), ssd1 :1568-1605, focal_loss_retina :1513-1530, smoothL1_loss_retina :1532-1566, SSD_loss.__call__
+// :1620-1644 and the autograd replay of all of it (General/Learner.py:514).
+//
+// Why one kernel.  The separate-kernel chain (background fill, sparse assignment, streaming loss, final reduction) spends
+// 17 us in its three small kernels -- pure latency -- which is 26 % of the Pascal-sized step (65.7 us) although the streaming
+// kernel itself runs at 85 % of the HBM roofline (profiles/r01_launches.csv).  Here:
+//   phase A  one WARP per ground-truth box (work handed out by an atomic ticket): the box's candidate windows per (level,
+//            base box), a cull of the image's other boxes against the windows' bounding box, then every candidate anchor
+//            is evaluated exactly like in rn_assign (float32(float64 base + shift), strict-fp32 IoU in ascending box
+//            order, first maximal index) and the owner box writes ONE BYTE per non-background anchor into a per-image
+//            byte map that is all-zero (= background) between launches.  No fill kernel, no [B,A] int32 array.
+//            While phase A runs (~5 us of dependent latencies) every CTA has already issued L2 prefetches for the first
+//            128 KB of its own slice of `clas`, so the otherwise idle HBM pipe is pulling the first ~50 MB of the step.
+//   phase B  every CTA streams one contiguous, 32-row aligned slice of the B*A anchor rows (all CTAs get the same number
+//            of rows, 3 CTAs per SM resident: no wave quantisation, no tail), image by image: it waits (acquire) until the
+//            image's boxes are done, then runs the element math of rn_loss.cu in chunks of whole rows; after each chunk the
+//            owner thread of a row computes its smooth-L1 term / d loss / d reg and re-zeroes the row's byte (the map is
+//            self-cleaning: the kernel leaves it as it found it).
+//   phase C  the last CTA to finish (one atomic per CTA: 444, not one per tile) sums the per-(CTA, image) partials in a
+//            fixed order in float64, normalises like the reference, writes {loss, reg_loss, clas_loss} and the positive
+//            counts, and resets the counters for the next launch.
+// Forward-progress: phase B waits only on phase-A work, and every phase-A task is taken (by ticket) by a warp that is
+// running and finishes it before its CTA ever waits -- no CTA depends on a CTA that has not been scheduled yet.
+// Determinism: the partition is a pure function of the shapes; all sums are fixed-order trees; no floating-point atomics.
+#include <string.h>
+
+#include "rn_loss_math.cuh"
+
+#define RN_STEP_CTAS 3                                // resident CTAs per SM (register bound, like rn_loss_kernel)
+#define RN_STEP_AWARPS 4                              // warps of a CTA that take phase-A box tasks
+#define RN_STEP_MAXSEG (RN_NUM_LEVELS * RN_MAX_K)     // candidate windows per box
+#define RN_STEP_MAXM 128                              // ground-truth slots per image the fused step supports
+#define RN_STEP_MAX_GRID 2048
+#define RN_STEP_ROW_ALIGN 32                          // CTA slices start at multiples of this many rows (>= 128 B of clas)
+#define RN_STEP_PF_BYTES (128 * 1024)                 // bytes of its slice a CTA prefetches into L2 before phase A
+
+struct RnStepCtrl {
+    int ticket_a;  // next phase-A task
+    int finished;  // CTAs that have written their partials
+    int err;       // bit 0: a ground-truth category >= C was seen
+    int pad;
+};
+
+struct RnStepWarpScratch {  // phase A, one per participating warp
+    int ix0[RN_STEP_MAXSEG], iy0[RN_STEP_MAXSEG], nw[RN_STEP_MAXSEG], pref[RN_STEP_MAXSEG + 1];
+    float4 cbox[RN_STEP_MAXM];
+    float carea[RN_STEP_MAXM];
+    unsigned char cidx[RN_STEP_MAXM];
+};
+
+struct RnStepParams {
+    RnLossParams L;          // clas, reg, gt_boxes, gt_cats, dclas, dreg, probs, B, A, C, CV, M, scalars (matches/npos/partials unused)
+    RnStepCtrl *ctrl;
+    int *done;               // [B] boxes of the image whose phase-A task has completed
+    int *npos_acc;           // [B] positives counted so far
+    uint8_t *m8;             // [B][A] 0 background, 255 ignored, 1 + matched box
+    double2 *partials;       // [grid][S] {sum of focal terms, sum of smooth-L1 terms} per (CTA, image of its slice)
+    float *per_image;        // [B][2]
+    float *out3;
+    int32_t *npos_out;       // [B] or NULL
+    int32_t *matches_out;    // [B][A] or NULL (inspection / tests)
+    long long total_rows, rpc;  // B*A; rows per CTA
+    int S;                   // partial slots per CTA
+    int chunk_rows;
+    int pf_bytes;
+    float pos_thr, neg_thr;
+    float w_reg, w_clas, bs;
+};
+
+__device__ __forceinline__ int rn_ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double rn_warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(RN_FULL_MASK, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase A: the assignment contribution of ONE ground-truth box, by one warp (see rn_assign_sparse_kernel in rn_assign.cu
+// for why the candidate windows are conservative; the arithmetic per candidate anchor is identical).
+// ------------------------------------------------------------------------------------------------
+static __device__ __noinline__ void rn_step_box_task(const RnStepParams &S, const RnGeom &g, int b, int row, RnStepWarpScratch &W) {
+    const int lane = threadIdx.x & 31;
+    const int M = S.L.M, K = g.K, nseg = RN_NUM_LEVELS * K;
+    const int64_t *cats = S.L.gt_cats + (size_t)b * M;
+    const float4 *boxes = S.L.gt_boxes + (size_t)b * M;
+    const long long cat = cats[row];
+    if (cat < 0) return;  // padding row (Vision.py:1637-1638); uniform over the warp
+    if (cat >= S.L.C && lane == 0) atomicOr(&S.ctrl->err, 1);  // the reference raises IndexError (Vision.py:1593)
+    const float4 me = boxes[row];
+    const double wg = (double)me.z - (double)me.x, hg = (double)me.w - (double)me.y;
+    // ---- candidate windows, one per (level, base box), and the bounding box of all their anchors ----
+    double ux1 = INFINITY, uy1 = INFINITY, ux2 = -INFINITY, uy2 = -INFINITY;
+    for (int sg = lane; sg < nseg; sg += 32) {
+        const int l = sg / K, k = sg - l * K;
+        int cx0 = 0, cy0 = 0, nw = 0, count = 0;
+        if (wg > 0.0 && hg > 0.0) {  // a degenerate box overlaps nothing
+            const double Ag = wg * hg, cxg = 0.5 * ((double)me.x + (double)me.z), cyg = 0.5 * ((double)me.y + (double)me.w);
+            const double tq = 0.95 * (double)S.neg_thr;
+            const double *bb = g.base + (l * RN_MAX_K + k) * 4;
+            const double wa = bb[2] - bb[0], ha = bb[3] - bb[1], Aa = wa * ha;
+            if (fmin(Aa, Ag) >= tq * fmax(Aa, Ag)) {              // IoU <= min(A)/max(A)
+                const double need = tq / (1.0 + tq) * (Aa + Ag);  // inter >= t/(1+t) * (Aa + Ag)
+                const double dx = 0.5 * (wa + wg) - need / fmin(ha, hg);
+                const double dy = 0.5 * (ha + hg) - need / fmin(wa, wg);
+                if (dx >= 0.0 && dy >= 0.0) {
+                    const double stride = (double)(8 << l), inv = 1.0 / stride;  // exact (power of two)
+                    const double gwd = (double)g.gw[l], ghd = (double)g.gh[l];
+                    const int ix0 = (int)fmin(gwd, fmax(0.0, ceil((cxg - dx) * inv - 0.51)));
+                    const int ix1 = (int)fmin(gwd - 1.0, fmax(-1.0, floor((cxg + dx) * inv - 0.49)));
+                    const int iy0 = (int)fmin(ghd, fmax(0.0, ceil((cyg - dy) * inv - 0.51)));
+                    const int iy1 = (int)fmin(ghd - 1.0, fmax(-1.0, floor((cyg + dy) * inv - 0.49)));
+                    if (ix1 >= ix0 && iy1 >= iy0) {
+                        cx0 = ix0;
+                        cy0 = iy0;
+                        nw = ix1 - ix0 + 1;
+                        count = nw * (iy1 - iy0 + 1);
+                        ux1 = fmin(ux1, ((double)ix0 + 0.5) * stride + bb[0]);
+                        uy1 = fmin(uy1, ((double)iy0 + 0.5) * stride + bb[1]);
+                        ux2 = fmax(ux2, ((double)ix1 + 0.5) * stride + bb[2]);
+                        uy2 = fmax(uy2, ((double)iy1 + 0.5) * stride + bb[3]);
+                    }
+                }
+            }
+        }
+        W.ix0[sg] = cx0;
+        W.iy0[sg] = cy0;
+        W.nw[sg] = nw;
+        W.pref[sg + 1] = count;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ux1 = fmin(ux1, __shfl_xor_sync(RN_FULL_MASK, ux1, o));
+        uy1 = fmin(uy1, __shfl_xor_sync(RN_FULL_MASK, uy1, o));
+        ux2 = fmax(ux2, __shfl_xor_sync(RN_FULL_MASK, ux2, o));
+        uy2 = fmax(uy2, __shfl_xor_sync(RN_FULL_MASK, uy2, o));
+    }
+    __syncwarp();
+    {   // inclusive scan of the window sizes (<= 80 entries)
+        int carry = 0;
+        for (int i0 = 0; i0 < nseg; i0 += 32) {
+            const int i = i0 + lane;
+            int v = (i < nseg) ? W.pref[i + 1] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(RN_FULL_MASK, v, o);
+                if (lane >= o) v += t;
+            }
+            if (i < nseg) W.pref[i + 1] = carry + v;
+            carry += __shfl_sync(RN_FULL_MASK, v, 31);
+        }
+        if (lane == 0) W.pref[0] = 0;
+    }
+    __syncwarp();
+    const int total = W.pref[nseg];
+    if (total == 0) return;
+    // ---- the image's boxes that touch the windows' bounding box, in ascending order (an exact cull: a box outside it has an
+    // intersection width or height <= 0, i.e. IoU exactly 0, with every candidate anchor; the float32 anchor coordinates
+    // are the roundings of values inside the float64 box, so rounding the box outwards keeps them inside) ----
+    const float bx1 = __double2float_rd(ux1), by1 = __double2float_rd(uy1), bx2 = __double2float_ru(ux2), by2 = __double2float_ru(uy2);
+    int nl = 0, nvalid = 0, self = 0;
+    for (int j0 = 0; j0 < M; j0 += 32) {
+        const int j = j0 + lane;
+        const bool valid = (j < M) && cats[j] >= 0;
+        const unsigned vmask = __ballot_sync(RN_FULL_MASK, valid);
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool hit = false;
+        if (valid) {
+            bx = boxes[j];
+            hit = (j == row) || (bx.z > bx1 && bx.x < bx2 && bx.w > by1 && bx.y < by2);
+        }
+        const unsigned hmask = __ballot_sync(RN_FULL_MASK, hit);
+        const unsigned lt = (1u << lane) - 1u;
+        if (hit) {
+            const int pos = nl + __popc(hmask & lt);
+            W.cbox[pos] = bx;
+            W.carea[pos] = rn_area(bx);
+            W.cidx[pos] = (unsigned char)(nvalid + __popc(vmask & lt));
+        }
+        if (row >= j0 && row < j0 + 32) self = nvalid + __popc(vmask & ((1u << (row - j0)) - 1u));
+        nl += __popc(hmask);
+        nvalid += __popc(vmask);
+    }
+    __syncwarp();
+    // ---- candidates ----
+    uint8_t *m8 = S.m8 + (size_t)b * g.A;
+    int cnt = 0;
+#pragma unroll 1
+    for (int idx = lane; idx < total; idx += 32) {
+        int seg = 0;  // largest seg with pref[seg] <= idx
+#pragma unroll
+        for (int step = 64; step > 0; step >>= 1)
+            if (seg + step < nseg && W.pref[seg + step] <= idx) seg += step;
+        const int l = seg / K, k = seg - l * K;
+        const int local = idx - W.pref[seg], nw = W.nw[seg];
+        const int iy = W.iy0[seg] + local / nw, ix = W.ix0[seg] + local % nw;
+        const double stride = (double)(8 << l);
+        const double sx = __dmul_rn((double)ix + 0.5, stride);  // retinanet.py:458 (exact)
+        const double sy = __dmul_rn((double)iy + 0.5, stride);  // retinanet.py:459
+        const double *bb = g.base + (l * RN_MAX_K + k) * 4;
+        float4 an;
+        an.x = __double2float_rn(__dadd_rn(bb[0], sx));
+        an.y = __double2float_rn(__dadd_rn(bb[1], sy));
+        an.z = __double2float_rn(__dadd_rn(bb[2], sx));
+        an.w = __double2float_rn(__dadd_rn(bb[3], sy));
+        const float aa = rn_area(an);
+        float best = 0.0f;  // IoU >= 0 and torch.max returns index 0 for an all-zero column
+        int bi = 0;
+        for (int q = 0; q < nl; ++q) {
+            const float4 gb = W.cbox[q];
+            const float iw = __fsub_rn(fminf(gb.z, an.z), fmaxf(gb.x, an.x));
+            const float ih = __fsub_rn(fminf(gb.w, an.w), fmaxf(gb.y, an.y));
+            if (iw > 0.0f && ih > 0.0f) {
+                const float inter = __fmul_rn(iw, ih);
+                const float uni = __fsub_rn(__fadd_rn(W.carea[q], aa), inter);  // Vision.py:255
+                const float v = __fdiv_rn(inter, uni);
+                if (v > best) {  // strict: first maximal index wins (torch.max, Vision.py:1505)
+                    best = v;
+                    bi = W.cidx[q];
+                }
+            }
+        }
+        if (bi != self) continue;  // another box's warp owns this anchor (or nothing overlaps it)
+        unsigned code = 255u;                       // ignored: max IoU in [neg_thr, pos_thr]
+        if (best > S.pos_thr) code = 1u + (unsigned)bi;  // Vision.py:1506, :1508-1509
+        else if (best < S.neg_thr) continue;        // background: already there (Vision.py:1507)
+        m8[g.off[l] + (iy * g.gw[l] + ix) * K + k] = (uint8_t)code;
+        cnt += (code != 255u);
+    }
+    cnt = __reduce_add_sync(RN_FULL_MASK, cnt);
+    if (lane == 0 && cnt) atomicAdd(S.npos_acc + b, cnt);  // integer: order independent
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase C: executed by the last CTA only.
+// ------------------------------------------------------------------------------------------------
+static __device__ __noinline__ void rn_step_final(const RnStepParams &S, float2 *s_img /* smem [<= cap] or NULL */) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int B = S.L.B, A = S.L.A;
+    const bool err = *reinterpret_cast<volatile int *>(&S.ctrl->err) != 0;
+#pragma unroll 2
+    for (int b = warp; b < B; b += RN_THREADS / 32) {
+        const long long r0 = (long long)b * A, r1 = r0 + A - 1;
+        const int c_lo = (int)(r0 / S.rpc), c_hi = (int)(r1 / S.rpc);
+        double cs = 0.0, rs = 0.0;
+        for (int c = c_lo + lane; c <= c_hi; c += 32) {
+            const int first_img = (int)(((long long)c * S.rpc) / A);
+            const double2 v = __ldcg(S.partials + (size_t)c * S.S + (b - first_img));
+            cs += v.x;
+            rs += v.y;
+        }
+        cs = rn_warp_sum_d(cs);
+        rs = rn_warp_sum_d(rs);
+        if (lane == 0) {
+            const int n = __ldcg(S.npos_acc + b);
+            const float n_norm = fmaxf((float)n, 1.0f);
+            float2 pi;
+            pi.x = n > 0 ? __fdiv_rn((float)rs, (float)(4 * n)) : 0.0f;  // reg loss of image b (mean over npos*4, Vision.py:1566)
+            pi.y = __fdiv_rn((float)cs, n_norm);                          // clas loss of image b (Vision.py:1530)
+            if (s_img) s_img[b] = pi;
+            else reinterpret_cast<float2 *>(S.per_image)[b] = pi;
+            if (S.npos_out) S.npos_out[b] = n;
+            S.npos_acc[b] = 0;  // leave the workspace as it was found
+            S.done[b] = 0;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float reg_total = 0.f, clas_total = 0.f;
+        for (int b = 0; b < B; ++b) {  // image order, fp32, like the reference's Python loop (Vision.py:1640-1641)
+            const float2 pi = s_img ? s_img[b] : reinterpret_cast<float2 *>(S.per_image)[b];
+            reg_total = __fadd_rn(reg_total, pi.x);
+            clas_total = __fadd_rn(clas_total, pi.y);
+        }
+        const float reg_loss = __fdiv_rn(reg_total, S.bs), clas_loss = __fdiv_rn(clas_total, S.bs);
+        float loss = __fadd_rn(__fmul_rn(S.w_reg, reg_loss), __fmul_rn(S.w_clas, clas_loss));
+        if (err) loss = __int_as_float(0x7fc00000);  // a category >= C: the reference raises; here the loss is poisoned
+        S.out3[0] = loss;
+        S.out3[1] = reg_loss;
+        S.out3[2] = clas_loss;
+        S.ctrl->ticket_a = 0;
+        S.ctrl->finished = 0;
+        S.ctrl->err = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase B, hot part: the class vectors [v0, v1) of image b (whole rows; a multiple of the sub-tile except at the end of a
+// slice).  Not inlined on purpose: the streaming loop then has the register file to itself (80 registers at 3 CTAs per SM,
+// like rn_loss_kernel) instead of sharing it with the loop control and accumulators of the persistent kernel around it.
+// Returns this thread's share of the focal sum.
+// ------------------------------------------------------------------------------------------------
+template <int V, int CVT, bool G2, bool GRAD, bool LOGITS>
+static __device__ __noinline__ float rn_step_chunk(const RnLossParams &P, int b, const uint8_t *__restrict__ m_img,
+                                                   const int *s_cat, int v0, int v1, float gl) {
+    const int CV = CVT ? CVT : P.CV;
+    const int nvec = P.A * CV;
+    const float *x_img = P.clas + (size_t)b * P.A * P.C;
+    float *dx_img = GRAD ? P.dclas + (size_t)b * P.A * P.C : nullptr;
+    float acc_neg = 0.0f, acc_pos = 0.0f;
+#pragma unroll 1
+    for (int tile0 = v0; tile0 < v1; tile0 += RN_LOSS_TILE) {
+        if (tile0 + RN_LOSS_TILE <= v1)
+            rn_loss_subtile<V, CVT, G2, GRAD, true, LOGITS, RnMatchU8>(P, b, x_img, dx_img, m_img, s_cat, CV, nvec, v1, tile0, gl, acc_neg, acc_pos);
+        else
+            rn_loss_subtile<V, CVT, G2, GRAD, false, LOGITS, RnMatchU8>(P, b, x_img, dx_img, m_img, s_cat, CV, nvec, v1, tile0, gl, acc_neg, acc_pos);
+    }
+    return acc_neg + acc_pos;
+}
+
+// Phase B, per-row part of a chunk: smooth L1 of the positive rows (Vision.py:1532-1566), d loss / d reg for every row, the
+// optional dense matches, and the self-cleaning of the byte map.  Returns this thread's share of the smooth-L1 sum.
+template <bool GRAD>
+static __device__ __noinline__ float rn_step_rows(const RnStepParams &S, const RnGeom &g, int b, int c0, int c1, float ge,
+                                                  const float4 *s_box) {
+    const int A = S.L.A;
+    uint8_t *m_img = S.m8 + (size_t)b * A;
+    const float4 *reg4 = reinterpret_cast<const float4 *>(S.L.reg) + (size_t)b * A;
+    float4 *dreg4 = GRAD ? reinterpret_cast<float4 *>(S.L.dreg) + (size_t)b * A : nullptr;
+    int32_t *mout = S.matches_out ? S.matches_out + (size_t)b * A : nullptr;
+    float acc_reg = 0.0f;
+    for (int row = c0 + (int)threadIdx.x; row < c1; row += RN_THREADS) {
+        unsigned code;
+        asm volatile("ld.global.u8 %0, [%1];" : "=r"(code) : "l"(m_img + row));
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (code != 0u) {
+            m_img[row] = 0;  // back to "background" for the next launch
+            if (code != 255u)
+                g4 = rn_smooth_l1_row(rn_anchor_from_param(g, nullptr, row), s_box[code - 1u], __ldg(reg4 + row), ge, acc_reg);
+        }
+        if (GRAD) dreg4[row] = g4;
+        if (mout) mout[row] = code == 0u ? RN_MATCH_NEG : (code == 255u ? RN_MATCH_IGNORE : (int)code - 1);
+    }
+    return acc_reg;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int V, int CVT, bool G2, bool GRAD, bool LOGITS>
+__global__ void __launch_bounds__(RN_THREADS, RN_STEP_CTAS)
+rn_step_kernel(const __grid_constant__ RnStepParams S, const __grid_constant__ RnGeom g) {
+    // phase A scratch and the phase B / C tables share this buffer (their lifetimes do not overlap)
+    __shared__ __align__(16) unsigned char s_raw[sizeof(RnStepWarpScratch) * RN_STEP_AWARPS];
+    __shared__ double s_red[2][RN_THREADS / 32];
+    __shared__ int s_last;
+    static_assert(sizeof(RnStepWarpScratch) * RN_STEP_AWARPS >= RN_STEP_MAXM * (sizeof(float4) + sizeof(int)), "phase B tables must fit");
+
+    const RnLossParams &P = S.L;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = P.A, C = P.C;
+    const int CV = CVT ? CVT : P.CV;
+    const int r_lo = (int)min((long long)blockIdx.x * S.rpc, S.total_rows);  // B*A < 2^31 is checked by the host
+    const int r_hi = (int)min((long long)r_lo + S.rpc, S.total_rows);
+
+    // L2 prefetch of the head of this CTA's slice of clas ([B*A, C] is contiguous over images): HBM works while phase A runs
+    if (r_lo < r_hi) {
+        const char *head = reinterpret_cast<const char *>(P.clas) + (size_t)r_lo * C * sizeof(float);
+        size_t bytes = (size_t)(r_hi - r_lo) * C * sizeof(float);
+        if (bytes > (size_t)S.pf_bytes) bytes = (size_t)S.pf_bytes;
+        for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)RN_THREADS * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(head + o));
+    }
+
+    // ---- phase A ----
+    if (warp < RN_STEP_AWARPS) {
+        RnStepWarpScratch &W = reinterpret_cast<RnStepWarpScratch *>(s_raw)[warp];
+        const int ntask = P.B * P.M;
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = atomicAdd(&S.ctrl->ticket_a, 1);
+            t = __shfl_sync(RN_FULL_MASK, t, 0);
+            if (t >= ntask) break;
+            const int b = t / P.M;
+            rn_step_box_task(S, g, b, t - b * P.M, W);
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();  // release: the bytes and the positive count of this box before the counter
+                atomicAdd(S.done + b, 1);
+            }
+        }
+    }
+
+    // ---- phase B ----
+    float4 *s_box = reinterpret_cast<float4 *>(s_raw);
+    int *s_cat = reinterpret_cast<int *>(s_box + RN_STEP_MAXM);
+    int seg = 0;
+#pragma unroll 1
+    for (int r = r_lo; r < r_hi; ++seg) {
+        const int b = r / A;
+        const int s0 = r - b * A;
+        const int s1 = min(A, r_hi - b * A);
+        if (tid == 0) {
+            while (rn_ld_acquire(S.done + b) < P.M) __nanosleep(64);
+        }
+        __syncthreads();  // the image's assignment is complete and visible; phase A scratch / previous image's tables are dead
+        if (tid < 32) rn_compact_gt(P.gt_boxes + (size_t)b * P.M, P.gt_cats + (size_t)b * P.M, P.M, s_box, nullptr, s_cat);
+        const int n_pos = *reinterpret_cast<volatile const int *>(S.npos_acc + b);
+        const float n_norm = fmaxf((float)n_pos, 1.0f);    // clamp(min=1), Vision.py:1530
+        const float gl = __fdiv_rn(P.wc_over_bs, n_norm);  // upstream of every focal term
+        const float ge = n_pos > 0 ? __fdiv_rn(P.wr_over_bs, (float)(4 * n_pos)) : 0.0f;  // mean() backward
+        const uint8_t *m_img = S.m8 + (size_t)b * A;
+        __syncthreads();  // s_box / s_cat visible
+
+        double d_clas = 0.0, d_reg = 0.0;
+#pragma unroll 1
+        for (int c0 = s0; c0 < s1; c0 += S.chunk_rows) {
+            const int c1 = min(s1, c0 + S.chunk_rows);
+            d_clas += (double)rn_step_chunk<V, CVT, G2, GRAD, LOGITS>(P, b, m_img, s_cat, c0 * CV, c1 * CV, gl);
+            __syncthreads();  // every thread has consumed its rows' bytes: the owners may now clean them
+            d_reg += (double)rn_step_rows<GRAD>(S, g, b, c0, c1, ge, s_box);
+        }
+        // ---- block reduction (fixed order) -> one partial pair per (CTA, image) ----
+        const double cw = rn_warp_sum_d(d_clas), rw = rn_warp_sum_d(d_reg);
+        if (lane == 0) {
+            s_red[0][warp] = cw;
+            s_red[1][warp] = rw;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double cs = 0.0, rs = 0.0;
+#pragma unroll
+            for (int w = 0; w < RN_THREADS / 32; ++w) {
+                cs += s_red[0][w];
+                rs += s_red[1][w];
+            }
+            S.partials[(size_t)blockIdx.x * S.S + seg] = make_double2(cs, rs);
+        }
+        r = b * A + s1;
+    }
+
+    // ---- phase C: the last CTA reduces ----
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();  // release this CTA's partials
+        s_last = (atomicAdd(&S.ctrl->finished, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();  // acquire the others'
+    rn_step_final(S, P.B * sizeof(float2) <= sizeof(s_raw) ? reinterpret_cast<float2 *>(s_raw) : nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+static inline size_t rn_up256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct RnStepWs {
+    size_t ctrl, done, npos_acc, m8, zero_end, partials, per_image, matches32, npos32, loss_ws, total;
+};
+static RnStepWs rn_step_layout(int B, int A, int C) {
+    RnStepWs w;
+    size_t o = 0;
+    w.ctrl = o;      o += rn_up256(sizeof(RnStepCtrl));
+    w.done = o;      o += rn_up256(sizeof(int) * (size_t)B);
+    w.npos_acc = o;  o += rn_up256(sizeof(int) * (size_t)B);
+    w.m8 = o;        o += rn_up256((size_t)B * (size_t)A);
+    w.zero_end = o;  // everything before this offset must be zero between launches
+    w.partials = o;  o += rn_up256(sizeof(double2) * ((size_t)B + 34 * (size_t)RN_STEP_MAX_GRID));
+    w.per_image = o; o += rn_up256(sizeof(float) * 2 * (size_t)B);
+    // the separate-kernel path (caller-supplied anchor tables, M > 128, unusual thresholds, rn_set_option("step_unfused"))
+    w.matches32 = o; o += rn_up256(sizeof(int32_t) * (size_t)B * (size_t)A);
+    w.npos32 = o;    o += rn_up256(sizeof(int32_t) * (size_t)B);
+    w.loss_ws = o;   o += rn_up256(rn_loss_workspace_bytes(B, A, C));
+    w.total = o;
+    return w;
+}
+
+extern "C" size_t rn_loss_step_workspace_bytes(int B, int A, int C) {
+    if (B <= 0 || A <= 0 || C <= 0) return 256;
+    return rn_step_layout(B, A, C).total;
+}
+
+extern "C" int rn_loss_step_workspace_init(void *workspace, size_t workspace_bytes, void *stream) {
+    if (!workspace || (((uintptr_t)workspace) & 255)) return rn_set_error(RN_ERR_WORKSPACE, "rn_loss_step_workspace_init: null or misaligned workspace");
+    cudaError_t e = cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_loss_step_workspace_init: %s", cudaGetErrorString(e));
+    return RN_OK;
+}
+
+// resident CTAs of a kernel on the current device (queried once per kernel and device)
+template <typename Kern>
+static int rn_step_max_grid(Kern kernel, int slot) {
+    static int cache[64][64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || slot < 0 || slot >= 64) return 148 * RN_STEP_CTAS;
+    if (cache[dev][slot] == 0) {
+        int per_sm = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RN_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 1;
+        int n = per_sm * sms;
+        cache[dev][slot] = n > RN_STEP_MAX_GRID ? RN_STEP_MAX_GRID : n;
+    }
+    return cache[dev][slot];
+}
+
+template <int V, int CVT, bool G2, bool GRAD, bool LOGITS>
+static int rn_step_launch(RnStepParams &S, const RnGeom &g, cudaStream_t s) {
+    auto kernel = rn_step_kernel<V, CVT, G2, GRAD, LOGITS>;
+    const int slot = ((V == 4 ? 0 : 1) * 3 + (CVT == 20 ? 0 : (CVT == 5 ? 1 : 2))) * 8 + (G2 ? 4 : 0) + (GRAD ? 2 : 0) + (LOGITS ? 1 : 0);
+    const int max_grid = rn_step_max_grid(kernel, slot);
+    const int CV = S.L.CV;
+    // rows per CTA: equal shares, a multiple of RN_STEP_ROW_ALIGN, at least one sub-tile of work
+    long long min_rows = (RN_LOSS_TILE + CV - 1) / CV;
+    long long rpc = (S.total_rows + max_grid - 1) / max_grid;
+    if (rpc < min_rows) rpc = min_rows;
+    rpc = (rpc + RN_STEP_ROW_ALIGN - 1) / RN_STEP_ROW_ALIGN * RN_STEP_ROW_ALIGN;
+    const int grid = (int)((S.total_rows + rpc - 1) / rpc);
+    S.rpc = rpc;
+    S.S = (int)((rpc + S.L.A - 1) / S.L.A) + 1;
+    // chunks of whole rows whose vector count is a multiple of the sub-tile (no partial sub-tile inside a slice)
+    int gcd = RN_LOSS_TILE, t = CV;
+    while (t) { const int q = gcd % t; gcd = t; t = q; }
+    S.chunk_rows = RN_LOSS_TILE / gcd;
+    while (S.chunk_rows * (long long)CV < 4LL * RN_LOSS_TILE) S.chunk_rows *= 2;
+    kernel<<<grid, RN_THREADS, 0, s>>>(S, g);
+    return rn_check_launch("rn_loss_step");
+}
+
+template <int V, int CVT, bool LOGITS>
+static int rn_step_dispatch(bool g2, bool grad, RnStepParams &S, const RnGeom &g, cudaStream_t s) {
+    if (g2 && grad) return rn_step_launch<V, CVT, true, true, LOGITS>(S, g, s);
+    // the rarer variants (forward only, gamma != 2) share the generic row width
+    if constexpr (CVT != 0) {
+        return rn_step_dispatch<V, 0, LOGITS>(g2, grad, S, g, s);
+    } else {
+        if (g2) return rn_step_launch<V, 0, true, false, LOGITS>(S, g, s);
+        if (grad) return rn_step_launch<V, 0, false, true, LOGITS>(S, g, s);
+        return rn_step_launch<V, 0, false, false, LOGITS>(S, g, s);
+    }
+}
+
+extern "C" int rn_loss_step(const float *clas, const float *reg, const float *gt_boxes, const int64_t *gt_cats, int B, int A,
+                            int C, int M, int H, int W, const double *base, int K, const float *anchors, float pos_thr,
+                            float neg_thr, double alpha, double gamma, double beta, int B_global, int from_logits,
+                            float *dclas, float *dreg, float *probs_out, float *out3, int32_t *npos_out,
+                            int32_t *matches_out, void *workspace, size_t workspace_bytes, void *stream) {
+    if (B <= 0 || A <= 0 || C <= 0 || M < 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: B=%d A=%d C=%d M=%d", B, A, C, M);
+    if (!clas || !reg || !out3 || (M > 0 && (!gt_boxes || !gt_cats))) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: null pointer");
+    if ((dclas == nullptr) != (dreg == nullptr))
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: dclas and dreg must both be given or both be NULL");
+    if (B_global < B) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: B_global=%d < B=%d", B_global, B);
+    const RnStepWs L = rn_step_layout(B, A, C);
+    if (!workspace || workspace_bytes < L.total || (((uintptr_t)workspace) & 255))
+        return rn_set_error(RN_ERR_WORKSPACE, "rn_loss_step: workspace needs %zu bytes, 256-byte aligned and zero-initialised", L.total);
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    cudaStream_t s = (cudaStream_t)stream;
+
+    const bool fused = !anchors && M >= 1 && M <= RN_STEP_MAXM && neg_thr >= 0.2f && pos_thr >= neg_thr && !rn_opt(RN_OPT_STEP_UNFUSED);
+    if (!fused) {  // the separate kernels: rn_assign (dense or sparse) + rn_loss
+        int32_t *m32 = matches_out ? matches_out : reinterpret_cast<int32_t *>(ws + L.matches32);
+        int32_t *n32 = npos_out ? npos_out : reinterpret_cast<int32_t *>(ws + L.npos32);
+        int rc = rn_assign(gt_boxes, gt_cats, B, M, H, W, base, K, anchors, A, pos_thr, neg_thr, m32, n32, nullptr, stream);
+        if (rc) return rc;
+        const size_t lw = rn_loss_workspace_bytes(B, A, C);
+        if (from_logits)
+            return rn_loss_logits(clas, reg, gt_boxes, gt_cats, m32, n32, B, A, C, M, H, W, base, K, anchors, alpha, gamma, beta,
+                                  B_global, dclas, dreg, probs_out, out3, ws + L.loss_ws, lw, stream);
+        return rn_loss(clas, reg, gt_boxes, gt_cats, m32, n32, B, A, C, M, H, W, base, K, anchors, alpha, gamma, beta, B_global,
+                       dclas, dreg, out3, ws + L.loss_ws, lw, stream);
+    }
+
+    const int V = (C % 4 == 0) ? 4 : 1;
+    if ((long long)A * (C / V) > 0x7fffffffLL - RN_LOSS_TILE) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: A*C too large");
+    if ((long long)B * A > 0x7fffffffLL - 4096) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: B*A too large");
+    if (V == 4 && ((((uintptr_t)clas) | ((uintptr_t)dclas) | ((uintptr_t)probs_out)) & 15))
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: clas/dclas/probs_out must be 16-byte aligned");
+    if ((((uintptr_t)reg) | ((uintptr_t)dreg) | ((uintptr_t)gt_boxes)) & 15)
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: reg/dreg/gt_boxes must be 16-byte aligned");
+    RnGeom g;
+    int rc = rn_build_geom(&g, H, W, base, K, nullptr, A);
+    if (rc) return rc;
+
+    RnStepParams S;
+    memset(&S, 0, sizeof(S));
+    RnLossParams &P = S.L;
+    P.clas = clas; P.reg = reg;
+    P.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); P.gt_cats = gt_cats;
+    P.dclas = dclas; P.dreg = dreg; P.probs = from_logits ? probs_out : nullptr;
+    P.B = B; P.A = A; P.C = C; P.CV = C / V; P.M = M;
+    P.a_pos = (float)alpha; P.a_neg = (float)(1.0 - alpha);  // Vision.py:1526
+    P.gamma = (float)gamma;
+    P.lo = (float)1e-4; P.hi = (float)(1.0 - 1e-4);          // Vision.py:1524
+    const float bs = (float)B_global;
+    S.w_reg = (float)(1.0 - beta); S.w_clas = (float)beta; S.bs = bs;  // Vision.py:1644
+    P.wc_over_bs = S.w_clas / bs;
+    P.wr_over_bs = S.w_reg / bs;
+    S.ctrl = reinterpret_cast<RnStepCtrl *>(ws + L.ctrl);
+    S.done = reinterpret_cast<int *>(ws + L.done);
+    S.npos_acc = reinterpret_cast<int *>(ws + L.npos_acc);
+    S.m8 = ws + L.m8;
+    S.partials = reinterpret_cast<double2 *>(ws + L.partials);
+    S.per_image = reinterpret_cast<float *>(ws + L.per_image);
+    S.out3 = out3; S.npos_out = npos_out; S.matches_out = matches_out;
+    S.total_rows = (long long)B * A;
+    S.pf_bytes = RN_STEP_PF_BYTES;
+    S.pos_thr = pos_thr; S.neg_thr = neg_thr;
+
+    const bool g2 = (gamma == 2.0), grad = dclas != nullptr;
+    if (from_logits) {
+        if (V == 4 && C == 80) return rn_step_dispatch<4, 20, true>(g2, grad, S, g, s);
+        if (V == 4 && C == 20) return rn_step_dispatch<4, 5, true>(g2, grad, S, g, s);
+        if (V == 4) return rn_step_dispatch<4, 0, true>(g2, grad, S, g, s);
+        return rn_step_dispatch<1, 0, true>(g2, grad, S, g, s);
+    }
+    if (V == 4 && C == 80) return rn_step_dispatch<4, 20, false>(g2, grad, S, g, s);
+    if (V == 4 && C == 20) return rn_step_dispatch<4, 5, false>(g2, grad, S, g, s);
+    if (V == 4) return rn_step_dispatch<4, 0, false>(g2, grad, S, g, s);
+    return rn_step_dispatch<1, 0, false>(g2, grad, S, g, s);
+}

@@ -18,6 +18,7 @@ from .core import ARR, TEN
 from .retinanet import anchor_args
 
 _ws = _lib.Workspace()
+_step_ws = _lib.Workspace(zeroed=True)   # rn_loss_step: zero-initialised once, left zeroed by every call
 
 
 def _targets(target, device):
@@ -49,8 +50,10 @@ def assign_batch(anchors, gt_boxes, gt_cats, pos_thresh=0.5, neg_thresh=0.4, wan
 
 
 def _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, need_grad, bufs=None):
-    """rn_assign + rn_loss on the current stream.  Returns (out3, dreg, dclas, matches, npos); `bufs` lets
-    a caller (CUDA-graph capture) supply persistent output tensors."""
+    """rn_loss_step on the current stream: assignment + loss forward/backward + final reduction, ONE kernel launch when
+    the anchors come from this package's AnchorGenerator (else the separate kernels, inside the same library call).
+    Returns (out3, dreg, dclas, matches, npos); `matches` is None unless cfg["keep_matches"]; `bufs` lets a caller
+    (CUDA-graph capture) supply persistent output tensors and the zero-initialised workspace."""
     lib = _lib.load()
     B, A, Cn = (int(v) for v in clas.shape)
     M = int(gt_cats.shape[1])
@@ -60,7 +63,7 @@ def _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, need_grad, bufs=Non
     if bufs is None:
         bufs = {}
     matches = bufs.get("matches")
-    if matches is None:
+    if matches is None and cfg.get("keep_matches"):
         matches = torch.empty((B, A), dtype=torch.int32, device=dev)
     npos = bufs.get("npos")
     if npos is None:
@@ -76,22 +79,26 @@ def _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, need_grad, bufs=Non
     out3 = bufs.get("out3")
     if out3 is None:
         out3 = torch.empty(3, dtype=torch.float32, device=dev)
-    ws = _ws.get(lib.rn_loss_workspace_bytes(B, A, Cn), dev)
-    stream = _lib.stream_ptr(dev)
-    _lib.check(lib.rn_assign(_lib.ptr(gt_boxes), _lib.ptr(gt_cats), B, M, H, W, base, K, table, A,
-                             float(cfg["pos_thresh"]), float(cfg["neg_thresh"]), _lib.ptr(matches), _lib.ptr(npos),
-                             None, stream))
-    common = (_lib.ptr(clas), _lib.ptr(reg), _lib.ptr(gt_boxes), _lib.ptr(gt_cats), _lib.ptr(matches), _lib.ptr(npos),
-              B, A, Cn, M, H, W, base, K, table, float(cfg["alpha"]), float(cfg["gamma"]), float(cfg["beta"]),
-              int(B_global), _lib.ptr(dclas), _lib.ptr(dreg))
-    tail = (_lib.ptr(out3), _lib.ptr(ws), ws.numel(), stream)
-    if cfg.get("from_logits"):
+    ws = bufs.get("ws")
+    if ws is None:
+        ws = _step_ws.get(lib.rn_loss_step_workspace_bytes(B, A, Cn), dev)
+    probs = None
+    from_logits = bool(cfg.get("from_logits"))
+    if from_logits:
         probs = torch.empty_like(clas) if cfg.get("want_probs") else None
         cfg["last_probs"] = probs
-        _lib.check(lib.rn_loss_logits(*(common + (_lib.ptr(probs),) + tail)))
-    else:
-        _lib.check(lib.rn_loss(*(common + tail)))
+    _lib.check(lib.rn_loss_step(_lib.ptr(clas), _lib.ptr(reg), _lib.ptr(gt_boxes), _lib.ptr(gt_cats), B, A, Cn, M, H, W,
+                                base, K, table, float(cfg["pos_thresh"]), float(cfg["neg_thresh"]), float(cfg["alpha"]),
+                                float(cfg["gamma"]), float(cfg["beta"]), int(B_global), int(from_logits), _lib.ptr(dclas),
+                                _lib.ptr(dreg), _lib.ptr(probs), _lib.ptr(out3), _lib.ptr(npos), _lib.ptr(matches),
+                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
     return out3, dreg, dclas, matches, npos
+
+
+def _step_is_fused(anchors, gt_cats, cfg):
+    """True when rn_loss_step runs as the single persistent kernel (see include/retina_b200.h)."""
+    return anchor_args(anchors)[4] is None and 1 <= int(gt_cats.shape[1]) <= 128 and cfg["neg_thresh"] >= 0.2 \
+        and cfg["pos_thresh"] >= cfg["neg_thresh"]
 
 
 class _SSDLossFunction(torch.autograd.Function):
@@ -112,6 +119,7 @@ class _SSDLossFunction(torch.autograd.Function):
         ctx.grads = (dreg, dclas)
         ctx.used = False
         cfg["last_matches"], cfg["last_npos"] = matches, npos
+        cfg["assign_inputs"] = (anchors, gt_boxes, gt_cats)   # for a lazy last_assignment
         loss, reg_loss, clas_loss = out3.unbind(0)
         ctx.mark_non_differentiable(reg_loss, clas_loss)
         return loss, reg_loss, clas_loss
@@ -236,14 +244,18 @@ class CapturedLossStep(object):
     def __init__(self, cfg, anchors, reg, clas, gt_boxes, gt_cats):
         dev = clas.device
         self.inputs = (anchors, reg, clas, gt_boxes, gt_cats)
+        self.cfg = cfg
         B, A, Cn = clas.shape
-        self.bufs = dict(matches=torch.empty((B, A), dtype=torch.int32, device=dev),
-                         npos=torch.empty((B,), dtype=torch.int32, device=dev),
+        lib = _lib.load()
+        self.bufs = dict(npos=torch.empty((B,), dtype=torch.int32, device=dev),
                          dclas=torch.empty_like(clas), dreg=torch.empty_like(reg),
-                         out3=torch.empty(3, dtype=torch.float32, device=dev))
+                         out3=torch.empty(3, dtype=torch.float32, device=dev),
+                         ws=torch.zeros(int(lib.rn_loss_step_workspace_bytes(int(B), int(A), int(Cn))), dtype=torch.uint8, device=dev))
+        if cfg.get("keep_matches"):
+            self.bufs["matches"] = torch.empty((B, A), dtype=torch.int32, device=dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):   # warm-up outside capture (workspace allocation, lazy module load)
+        with torch.cuda.stream(side):   # warm-up outside capture (lazy module load)
             _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, True, self.bufs)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
@@ -253,12 +265,23 @@ class CapturedLossStep(object):
         self.out3 = self.bufs["out3"]
         self.loss, self.reg_loss, self.clas_loss = self.out3.unbind(0)
         self.dreg, self.dclas = self.bufs["dreg"], self.bufs["dclas"]
-        self.matches, self.npos = self.bufs["matches"], self.bufs["npos"]
-        # sparse assignment (generated anchors, 1 <= M <= 128, default thresholds): rn_assign_fill_kernel,
-        # rn_assign_sparse_kernel, rn_loss_kernel, rn_loss_final_kernel; dense: rn_assign_kernel (+ a memset node), loss, final
-        sparse = anchor_args(anchors)[4] is None and 1 <= int(gt_cats.shape[1]) <= 128 and cfg["neg_thresh"] >= 0.2 \
-            and cfg["pos_thresh"] >= cfg["neg_thresh"]
-        self.kernels_per_replay = 4 if sparse else 3
+        self.npos = self.bufs["npos"]
+        # fused: rn_step_kernel only.  Otherwise rn_assign (fill + sparse, or a memset node + dense), loss, final reduction.
+        if _step_is_fused(anchors, gt_cats, cfg):
+            self.kernels_per_replay = 1
+        else:
+            sparse = anchor_args(anchors)[4] is None and 1 <= int(gt_cats.shape[1]) <= 128 and cfg["neg_thresh"] >= 0.2 \
+                and cfg["pos_thresh"] >= cfg["neg_thresh"]
+            self.kernels_per_replay = 4 if sparse else 3
+
+    @property
+    def matches(self):
+        """[B,A] int32 assignment of the static inputs: the step's own output when the loss was built with
+        keep_matches=True, else computed on demand by rn_assign."""
+        if "matches" in self.bufs:
+            return self.bufs["matches"]
+        anchors, _, _, gt_boxes, gt_cats = self.inputs
+        return assign_batch(anchors, gt_boxes, gt_cats, self.cfg["pos_thresh"], self.cfg["neg_thresh"])[0]
 
     def replay(self):
         self.graph.replay()
@@ -317,9 +340,12 @@ class SSD_loss(object):
     12-byte NCCL exchange; per-rank reg/clas gradients need no communication."""
 
     def __init__(self, beta=0.5, alpha=0.25, gamma=2.0, distributed=False, process_group=None, global_batch=None,
-                 from_logits=False, keep_probs=False):
+                 from_logits=False, keep_probs=False, keep_matches=False):
         self.beta, self.alpha, self.gamma = beta, alpha, gamma
         self.keep_probs = bool(keep_probs)   # from_logits only: also store sigmoid(logits) in .last_probs
+        # keep_matches: the step also writes its dense [bs,A] int32 assignment (4*A*bs bytes of extra stores; for
+        # inspection and tests).  Without it last_assignment computes the matches on demand with rn_assign.
+        self.keep_matches = bool(keep_matches)
         # from_logits=True: `clas` holds logits and the head's nn.Sigmoid (reference retinanet.py:258,286) is
         # fused into the loss kernel (SURVEY.md section 8f row 1; needs a head that returns logits)
         self.from_logits = bool(from_logits)
@@ -344,7 +370,8 @@ class SSD_loss(object):
             world = dist.get_world_size(self.process_group)
         cfg = dict(alpha=self.alpha, gamma=self.gamma, beta=self.beta, pos_thresh=self.pos_thresh,
                    neg_thresh=self.neg_thresh, world_size=world, group=self.process_group,
-                   global_batch=self.global_batch, from_logits=self.from_logits, want_probs=self.keep_probs)
+                   global_batch=self.global_batch, from_logits=self.from_logits, want_probs=self.keep_probs,
+                   keep_matches=self.keep_matches)
         loss, reg_loss, clas_loss = _SSDLossFunction.apply(reg.contiguous(), clas.contiguous(), anchors, gt_boxes,
                                                            gt_cats, cfg)
         self._cfg = cfg
@@ -392,7 +419,7 @@ class SSD_loss(object):
                 raise ValueError("capture() needs contiguous static tensors")
         cfg = dict(alpha=self.alpha, gamma=self.gamma, beta=self.beta, pos_thresh=self.pos_thresh,
                    neg_thresh=self.neg_thresh, world_size=1, group=None, global_batch=self.global_batch,
-                   from_logits=self.from_logits)
+                   from_logits=self.from_logits, keep_matches=self.keep_matches)
         return CapturedLossStep(cfg, anchors, reg.detach(), clas.detach(), BBoxes, Cats)
 
     @property
@@ -402,8 +429,15 @@ class SSD_loss(object):
 
     @property
     def last_assignment(self):
-        """(matches [bs,A] int32, npos [bs] int32) of the most recent call (device tensors)."""
-        return self._cfg.get("last_matches"), self._cfg.get("last_npos")
+        """(matches [bs,A] int32, npos [bs] int32) of the most recent call (device tensors).  npos is always the step's
+        own count; matches is the step's own output with keep_matches=True (or on the level-tensor path) and is otherwise
+        computed here, on demand, by rn_assign on the same targets."""
+        matches, npos = self._cfg.get("last_matches"), self._cfg.get("last_npos")
+        if matches is None and self._cfg.get("assign_inputs") is not None:
+            anchors, gt_boxes, gt_cats = self._cfg["assign_inputs"]
+            matches = assign_batch(anchors, gt_boxes, gt_cats, self._cfg["pos_thresh"], self._cfg["neg_thresh"])[0]
+            self._cfg["last_matches"] = matches
+        return matches, npos
 
 
 class SSD_RegLoss(object):

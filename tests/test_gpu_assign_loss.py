@@ -134,7 +134,7 @@ def test_max_overlaps_metric():
 
 def run_loss(anchors, clas, reg, gb, gc, upstream=None, **kw):
     from neuralnetworklibrary_b200.vision import SSD_loss
-    f = SSD_loss(**kw)
+    f = SSD_loss(keep_matches=True, **kw)   # the assignment checked below is the fused step's own output
     cd = clas.to(dev()).requires_grad_(True)
     rd = reg.to(dev()).requires_grad_(True)
     loss = f([anchors, rd, cd], [gb.to(dev()), gc.to(dev())])
@@ -257,7 +257,7 @@ def test_captured_step_matches_eager():
         data.append((clas, reg, gb, gc))
     clas_s, reg_s = data[0][0].to(dev()), data[0][1].to(dev())
     gb_s, gc_s = data[0][2].to(dev()), data[0][3].to(dev())
-    cap = SSD_loss().capture([anchors, reg_s, clas_s], [gb_s, gc_s])
+    cap = SSD_loss(keep_matches=True).capture([anchors, reg_s, clas_s], [gb_s, gc_s])
     for clas, reg, gb, gc in data:
         clas_s.copy_(clas.to(dev()))
         reg_s.copy_(reg.to(dev()))

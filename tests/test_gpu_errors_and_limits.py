@@ -73,7 +73,7 @@ def test_other_anchor_sets(ratios, scales):
     assert np.array_equal(anchors.cpu().numpy(), an)
     gb, gc = syn.make_targets(B, M, H, W, C, seed=7, min_side=10.0, max_frac=0.7)
     clas, reg = syn.make_train_activations(B, an.shape[0], C, seed=7)
-    f = SSD_loss()
+    f = SSD_loss(keep_matches=True)
     cd, rd = clas.to(dev()).requires_grad_(True), reg.to(dev()).requires_grad_(True)
     loss = f([anchors, rd, cd], [gb.to(dev()), gc.to(dev())])
     loss.backward()

@@ -33,7 +33,7 @@ def test_random_loss_configs(case):
     gb, gc = syn.make_targets(B, M, H, W, C, seed=case, force_empty_and_full=bool(rng.randint(2)), min_side=6.0,
                               max_frac=0.9)
     clas, reg = syn.make_train_activations(B, an.shape[0], C, seed=case, mu=float(rng.uniform(-5, -1)), edge_cases=64)
-    f = SSD_loss(**kw)
+    f = SSD_loss(keep_matches=bool(case % 2), **kw)   # odd cases: the step's own matches; even: rn_assign on demand
     cd, rd = clas.to(dev()).requires_grad_(True), reg.to(dev()).requires_grad_(True)
     loss = f([anchors, rd, cd], [gb.to(dev()), gc.to(dev())])
     loss.backward()

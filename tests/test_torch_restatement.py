@@ -95,7 +95,7 @@ def test_kernels_vs_restatement_on_cuda_loss(seed, H, W, C, B, M, kw):
     out3, dclas, dreg, matches = _restated_loss(an, clas, reg, gb, gc, device=dev, **kw)
     anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=dev))
     cd, rd = clas.to(dev).requires_grad_(True), reg.to(dev).requires_grad_(True)
-    f = SSD_loss(**kw)
+    f = SSD_loss(keep_matches=True, **kw)
     loss = f([anchors, rd, cd], [gb.to(dev), gc.to(dev)])
     loss.backward()
     got_m, _ = f.last_assignment
