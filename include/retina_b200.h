@@ -57,7 +57,7 @@ int rn_abi_version(void);
 /* Process-wide tuning / test switches (all default 0; nothing is ever read from the environment).  Names:
  *   "assign_dense" (!= 0: rn_assign always takes the dense kernel), "assign_no_balance", "assign_wbase" (dense kernel work
  *   balancing), "loss_iters" (> 0: sub-tiles per CTA of rn_loss), "levels_nchunks" (> 0: class chunks per row tile of
- *   rn_loss_levels), "step_unfused" (!= 0: rn_loss_step launches the separate assignment / loss / reduction kernels).
+ *   rn_loss_levels), "step_fused" (!= 0: rn_loss_step runs as one persistent kernel where its conditions hold).
  * rn_set_option returns RN_ERR_INVALID_ARG for an unknown name; rn_get_option returns -1 for one. */
 int rn_set_option(const char *name, int value);
 int rn_get_option(const char *name);
@@ -126,18 +126,23 @@ int rn_loss(const float *clas, const float *reg, const float *gt_boxes, const in
  * (General/Learner.py:514).  Same inputs, outputs and numerics as the two separate calls; pos_thr / neg_thr are the
  * thresholds of match_anchors_objects (0.5 / 0.4).  npos_out [B] (positives per image) and matches_out [B,A] (the
  * rn_assign encoding; costs 4*A*B bytes of stores, meant for inspection and tests) may be NULL.
- * With generated anchors (anchors == NULL), 1 <= M <= 128 and 0.2 <= neg_thr <= pos_thr the step is a single persistent
- * kernel (rn_step.cu): one warp per ground-truth box writes a byte per non-background anchor, the CTAs stream equal slices
- * of the B*A rows and the last CTA reduces; otherwise (or after rn_set_option("step_unfused", 1)) the separate kernels run.
- * The workspace (rn_loss_step_workspace_bytes, 256-byte aligned) must be ZERO-INITIALISED once before its first use
- * (rn_loss_step_workspace_init, or any memset) and every call leaves it zeroed again; one workspace per stream. */
+ * By default the call launches the separate kernels (sparse or dense assignment, streaming loss, final reduction: the
+ * fastest variant measured, profiles/r02_summary.md).  After rn_set_option("step_fused", 1), with generated anchors
+ * (anchors == NULL), 1 <= M <= 128 and 0.2 <= neg_thr <= pos_thr, the step is a single persistent kernel (rn_step.cu):
+ * warps take ground-truth boxes by ticket and write one byte per non-background anchor, the CTAs draw chunks of the B*A
+ * rows by ticket, and the last CTA reduces.
+ * Two caller-owned buffers, both 256-byte aligned, one pair per stream: `workspace` (rn_loss_step_workspace_bytes) is
+ * plain scratch; `state` (rn_loss_step_state_bytes) must be ZERO-INITIALISED once before its first use
+ * (rn_loss_step_state_init, or any memset) and every call leaves it all-zero again, whatever the shapes -- so one
+ * grow-only zeroed buffer serves calls of any shape. */
 size_t rn_loss_step_workspace_bytes(int B, int A, int C);
-int rn_loss_step_workspace_init(void *workspace, size_t workspace_bytes, void *stream);
+size_t rn_loss_step_state_bytes(int B, int A);
+int rn_loss_step_state_init(void *state, size_t state_bytes, void *stream);
 int rn_loss_step(const float *clas, const float *reg, const float *gt_boxes, const int64_t *gt_cats, int B, int A,
                  int C, int M, int H, int W, const double *base /*host*/, int K, const float *anchors /*or NULL*/,
                  float pos_thr, float neg_thr, double alpha, double gamma, double beta, int B_global, int from_logits,
                  float *dclas, float *dreg, float *probs_out, float *out3, int32_t *npos_out, int32_t *matches_out,
-                 void *workspace, size_t workspace_bytes, void *stream);
+                 void *state, size_t state_bytes, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Same as rn_loss, but the class activations are LOGITS: the head's nn.Sigmoid (retinanet.py:258, :286) is
  * fused into the kernel (y = 1/(1+exp(-z)) within ~5 ulp of the correctly rounded value) and

@@ -66,7 +66,8 @@ def build_library(force=False, verbose=False):
         path = os.path.join(_PKG, "csrc", src)
         obj = os.path.join(BUILD_DIR, src[:-3] + ".o")
         if force or _newer([path] + _headers(), obj):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, path]
+            extra = os.environ.get("RN_EXTRA_NVCC_FLAGS", "").split()   # build-time only (e.g. -DRN_STEP_TIMING for profiles/step_timing.py)
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, path]
             jobs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, proc in jobs:
         out, _ = proc.communicate()
@@ -111,10 +112,11 @@ PROTOTYPES = {
                                  C.c_int, _f64p, C.c_int, _f32p, C.c_double, C.c_double, C.c_double, C.c_int,
                                  _f32p, _f32p, _f32p, _f32p, _vp, C.c_size_t, _vp]),
     "rn_loss_step_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
-    "rn_loss_step_workspace_init": (C.c_int, [_vp, C.c_size_t, _vp]),
+    "rn_loss_step_state_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "rn_loss_step_state_init": (C.c_int, [_vp, C.c_size_t, _vp]),
     "rn_loss_step": (C.c_int, [_f32p, _f32p, _f32p, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int,
                                _f32p, C.c_float, C.c_float, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
-                               _f32p, _f32p, _f32p, _f32p, _i32p, _i32p, _vp, C.c_size_t, _vp]),
+                               _f32p, _f32p, _f32p, _f32p, _i32p, _i32p, _vp, C.c_size_t, _vp, C.c_size_t, _vp]),
     "rn_scale_grads": (C.c_int, [_f32p, C.c_size_t, _f32p, C.c_size_t, _f32p, _vp]),
     "rn_postproc_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rn_postproc": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _f32p,

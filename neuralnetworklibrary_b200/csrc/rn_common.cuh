@@ -41,7 +41,7 @@ enum RnOption {
     RN_OPT_ASSIGN_WBASE,       // > 0: base weight of an image in the dense kernel's balancing (default 11)
     RN_OPT_LOSS_ITERS,         // > 0: sub-tiles per CTA of the flat loss kernel
     RN_OPT_LVL_NCHUNKS,        // > 0: class chunks per row tile of the level-tensor loss
-    RN_OPT_STEP_UNFUSED,       // != 0: rn_loss_step runs the separate assignment / loss / reduction kernels
+    RN_OPT_STEP_FUSED,         // != 0: rn_loss_step runs as ONE persistent kernel (rn_step.cu) where its conditions hold
     RN_OPT_COUNT
 };
 int rn_opt(int id);

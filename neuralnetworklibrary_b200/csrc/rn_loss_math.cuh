@@ -279,13 +279,18 @@ __device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, int b, co
 #pragma unroll
     for (int u = 0; u < RN_LOSS_U; ++u) {
         const int v = v0 + u * RN_THREADS;
-        if (FULL || v < vend) {
+        if (FULL) {
             xv[u].load(xp + (size_t)u * RN_THREADS * V);
             mrow[u] = MT::load(m_img, v / CV);
         } else {
-            mrow[u] = RN_MATCH_IGNORE;
-#pragma unroll
-            for (int e = 0; e < V; ++e) xv[u].at(e) = 0.5f;
+            // Ragged end of a range: the loads stay UNCONDITIONAL (a vector past the end re-reads the last valid one), so all U
+            // requests are in flight together as in the full sub-tile; the vector is then treated as an ignored row (its terms
+            // are exactly zero) and its stores are predicated off.  A branch per load would serialise them.
+            const bool ok = v < vend;
+            const int vc = ok ? v : vend - 1;
+            xv[u].load(x_img + (size_t)vc * V);
+            const int mm = MT::load(m_img, vc / CV);
+            mrow[u] = ok ? mm : RN_MATCH_IGNORE;
         }
     }
     float *dp = GRAD ? dx_img + (size_t)v0 * V : nullptr;

@@ -18,7 +18,7 @@ from .core import ARR, TEN
 from .retinanet import anchor_args
 
 _ws = _lib.Workspace()
-_step_ws = _lib.Workspace(zeroed=True)   # rn_loss_step: zero-initialised once, left zeroed by every call
+_step_state = _lib.Workspace(zeroed=True)   # rn_loss_step's state buffer: zero-initialised once, left zeroed by every call
 
 
 def _targets(target, device):
@@ -50,8 +50,8 @@ def assign_batch(anchors, gt_boxes, gt_cats, pos_thresh=0.5, neg_thresh=0.4, wan
 
 
 def _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, need_grad, bufs=None):
-    """rn_loss_step on the current stream: assignment + loss forward/backward + final reduction, ONE kernel launch when
-    the anchors come from this package's AnchorGenerator (else the separate kernels, inside the same library call).
+    """rn_loss_step on the current stream: assignment + loss forward/backward + final reduction in one library call (the
+    separate kernels by default, ONE persistent kernel after rn_set_option("step_fused", 1)).
     Returns (out3, dreg, dclas, matches, npos); `matches` is None unless cfg["keep_matches"]; `bufs` lets a caller
     (CUDA-graph capture) supply persistent output tensors and the zero-initialised workspace."""
     lib = _lib.load()
@@ -81,7 +81,10 @@ def _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, need_grad, bufs=Non
         out3 = torch.empty(3, dtype=torch.float32, device=dev)
     ws = bufs.get("ws")
     if ws is None:
-        ws = _step_ws.get(lib.rn_loss_step_workspace_bytes(B, A, Cn), dev)
+        ws = _ws.get(lib.rn_loss_step_workspace_bytes(B, A, Cn), dev)
+    state = bufs.get("state")
+    if state is None:
+        state = _step_state.get(lib.rn_loss_step_state_bytes(B, A), dev)
     probs = None
     from_logits = bool(cfg.get("from_logits"))
     if from_logits:
@@ -91,14 +94,15 @@ def _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, need_grad, bufs=Non
                                 base, K, table, float(cfg["pos_thresh"]), float(cfg["neg_thresh"]), float(cfg["alpha"]),
                                 float(cfg["gamma"]), float(cfg["beta"]), int(B_global), int(from_logits), _lib.ptr(dclas),
                                 _lib.ptr(dreg), _lib.ptr(probs), _lib.ptr(out3), _lib.ptr(npos), _lib.ptr(matches),
-                                _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+                                _lib.ptr(state), state.numel(), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
     return out3, dreg, dclas, matches, npos
 
 
 def _step_is_fused(anchors, gt_cats, cfg):
-    """True when rn_loss_step runs as the single persistent kernel (see include/retina_b200.h)."""
-    return anchor_args(anchors)[4] is None and 1 <= int(gt_cats.shape[1]) <= 128 and cfg["neg_thresh"] >= 0.2 \
-        and cfg["pos_thresh"] >= cfg["neg_thresh"]
+    """True when rn_loss_step runs as the single persistent kernel (opt-in: rn_set_option("step_fused", 1); see
+    include/retina_b200.h)."""
+    return _lib.load().rn_get_option(b"step_fused") > 0 and anchor_args(anchors)[4] is None \
+        and 1 <= int(gt_cats.shape[1]) <= 128 and cfg["neg_thresh"] >= 0.2 and cfg["pos_thresh"] >= cfg["neg_thresh"]
 
 
 class _SSDLossFunction(torch.autograd.Function):
@@ -250,7 +254,8 @@ class CapturedLossStep(object):
         self.bufs = dict(npos=torch.empty((B,), dtype=torch.int32, device=dev),
                          dclas=torch.empty_like(clas), dreg=torch.empty_like(reg),
                          out3=torch.empty(3, dtype=torch.float32, device=dev),
-                         ws=torch.zeros(int(lib.rn_loss_step_workspace_bytes(int(B), int(A), int(Cn))), dtype=torch.uint8, device=dev))
+                         ws=torch.empty(int(lib.rn_loss_step_workspace_bytes(int(B), int(A), int(Cn))), dtype=torch.uint8, device=dev),
+                         state=torch.zeros(int(lib.rn_loss_step_state_bytes(int(B), int(A))), dtype=torch.uint8, device=dev))
         if cfg.get("keep_matches"):
             self.bufs["matches"] = torch.empty((B, A), dtype=torch.int32, device=dev)
         side = torch.cuda.Stream(device=dev)

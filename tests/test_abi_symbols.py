@@ -32,7 +32,7 @@ def test_host_only_entry_points():
     assert lib.rn_get_option(b"assign_dense") == 0 and lib.rn_get_option(b"no_such_option") == -1
     assert lib.rn_set_option(b"no_such_option", 1) == _lib.RN_ERR_INVALID_ARG
     assert lib.rn_set_option(b"loss_iters", 2) == 0 and lib.rn_get_option(b"loss_iters") == 2 and lib.rn_set_option(b"loss_iters", 0) == 0
-    assert lib.rn_loss_step_workspace_bytes(16, 201600, 80) % 256 == 0 and lib.rn_loss_step_workspace_bytes(16, 201600, 80) >= 16 * 201600
+    assert lib.rn_loss_step_workspace_bytes(16, 201600, 80) % 256 == 0 and lib.rn_loss_step_state_bytes(16, 201600) >= 16 * 201600
     assert lib.rn_num_anchors(512, 512, 9) == 49104
     assert lib.rn_num_anchors(800, 1333, 9) == 200700
     assert lib.rn_num_anchors(800, 1344, 9) == 201600
@@ -71,8 +71,8 @@ def test_argument_validation_returns_error_codes_without_a_device():
     assert lib.rn_map_match(None, None, None, None, None, None, 1, 1, None, 0, None, None) == INVALID
     assert lib.rn_assign(None, None, 2, 4, 64, 64, None, 9, None, 100, 0.5, 0.4, None, None, None, None) == INVALID
     assert lib.rn_loss_step(None, None, None, None, 2, 100, 20, 4, 64, 64, None, 9, None, 0.5, 0.4, 0.25, 2.0, 0.5, 2, 0,
-                            None, None, None, None, None, None, None, 0, None) == INVALID
-    assert lib.rn_loss_step_workspace_init(None, 0, None) == WORKSPACE
+                            None, None, None, None, None, None, None, 0, None, 0, None) == INVALID
+    assert lib.rn_loss_step_state_init(None, 0, None) == WORKSPACE
     # top_k outside the supported range, workspace too small
     import numpy as np
     f4 = (ctypes.c_float * 4)(0, 0, 0, 0)
@@ -84,4 +84,4 @@ def test_argument_validation_returns_error_codes_without_a_device():
                        _lib.base_ptr(base), 9, None, 0.25, 2.0, 0.5, 2, None, None, dummy, dummy, 16, None) == WORKSPACE
     assert b"workspace" in lib.rn_last_error()
     assert lib.rn_loss_step(dummy, dummy, dummy, dummy, 2, lib.rn_num_anchors(64, 64, 9), 20, 4, 64, 64, _lib.base_ptr(base), 9,
-                            None, 0.5, 0.4, 0.25, 2.0, 0.5, 2, 0, None, None, None, dummy, None, None, dummy, 16, None) == WORKSPACE
+                            None, 0.5, 0.4, 0.25, 2.0, 0.5, 2, 0, None, None, None, dummy, None, None, dummy, 16, dummy, 16, None) == WORKSPACE

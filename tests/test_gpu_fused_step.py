@@ -1,8 +1,8 @@
-"""The fused training step (rn_loss_step -> rn_step_kernel: assignment + loss forward/backward + final reduction in one
-persistent launch) against the separate kernels of the same library (rn_set_option("step_unfused", 1): rn_assign + rn_loss)
+"""The fused training step (rn_loss_step after rn_set_option("step_fused", 1) -> rn_step_kernel: assignment + loss
+forward/backward + final reduction in one persistent launch) against the separate kernels of the same library (the default)
 and against the CPU oracle.  Assignments and positive counts bit-exact, gradients BIT-IDENTICAL to the separate kernels (same
 element arithmetic), the three loss scalars within 1e-6 of them (the partial sums are grouped differently) and rtol 1e-5 of
-the oracle.  Also: the zero-initialised workspace is left zeroed (self-cleaning byte map), many boxes, boxes far outside
+the oracle.  Also: the zero-initialised state buffer is left zeroed (self-cleaning byte map), calls of different shapes share it, many boxes, boxes far outside
 the image, an image without objects in the middle of a batch, and the poisoned loss for a category >= C."""
 import numpy as np
 import pytest
@@ -27,7 +27,7 @@ def anchors_for(H, W):
 def run(anchors, clas, reg, gb, gc, unfused=False, **kw):
     from neuralnetworklibrary_b200 import _lib
     from neuralnetworklibrary_b200.vision import SSD_loss
-    with _lib.option("step_unfused", 1 if unfused else 0):
+    with _lib.option("step_fused", 0 if unfused else 1):
         f = SSD_loss(keep_matches=True, **kw)
         cd, rd = clas.to(dev()).requires_grad_(True), reg.to(dev()).requires_grad_(True)
         loss = f([anchors, rd, cd], [gb.to(dev()), gc.to(dev())])
@@ -91,10 +91,9 @@ def test_fused_step_is_repeatable_and_leaves_workspace_zeroed():
                 assert np.array_equal(a, b)
         else:
             first[seed] = o
-    ws = vision._step_ws.get(_lib.load().rn_loss_step_workspace_bytes(B, A, C), dev())
+    state = vision._step_state.get(_lib.load().rn_loss_step_state_bytes(B, A), dev())
     torch.cuda.synchronize()
-    zero_end = 256 + 2 * (((4 * B + 255) // 256) * 256) + ((B * A + 255) // 256) * 256   # ctrl | done | npos_acc | byte map
-    assert not ws[:zero_end].any(), "the step left residue in its workspace"
+    assert not state.any(), "the step left residue in its state buffer"
 
 
 def test_fused_step_no_grad_and_logits():
@@ -103,33 +102,36 @@ def test_fused_step_no_grad_and_logits():
     anchors, an = anchors_for(H, W), orc.anchors(H, W)
     gb, gc = syn.make_targets(B, M, H, W, C, seed=611)
     clas, reg = syn.make_train_activations(B, an.shape[0], C, seed=611)
+    from neuralnetworklibrary_b200 import _lib
     base = run(anchors, clas, reg, gb, gc)
-    with torch.no_grad():
-        f = SSD_loss()
-        loss = f([anchors, reg.to(dev()), clas.to(dev())], [gb.to(dev()), gc.to(dev())])
-    assert loss.item() == base[0][0] and not loss.requires_grad
-    # logits in: the loss value on sigmoid(logits) as the kernel computed them equals the probability path bit for bit
-    logits = torch.logit(clas.clamp(1e-6, 1 - 1e-6))
-    fl = SSD_loss(from_logits=True, keep_probs=True)
-    ld = logits.to(dev()).requires_grad_(True)
-    l1 = fl([anchors, reg.to(dev()), ld], [gb.to(dev()), gc.to(dev())])
-    l1.backward()
-    with torch.no_grad():
-        l2 = SSD_loss()([anchors, reg.to(dev()), fl.last_probs], [gb.to(dev()), gc.to(dev())])
-    assert l1.item() == l2.item() and torch.isfinite(ld.grad).all()
+    with _lib.option("step_fused", 1):
+        with torch.no_grad():
+            f = SSD_loss()
+            loss = f([anchors, reg.to(dev()), clas.to(dev())], [gb.to(dev()), gc.to(dev())])
+        assert loss.item() == base[0][0] and not loss.requires_grad
+        # logits in: the loss value on sigmoid(logits) as the kernel computed them equals the probability path bit for bit
+        logits = torch.logit(clas.clamp(1e-6, 1 - 1e-6))
+        fl = SSD_loss(from_logits=True, keep_probs=True)
+        ld = logits.to(dev()).requires_grad_(True)
+        l1 = fl([anchors, reg.to(dev()), ld], [gb.to(dev()), gc.to(dev())])
+        l1.backward()
+        with torch.no_grad():
+            l2 = SSD_loss()([anchors, reg.to(dev()), fl.last_probs], [gb.to(dev()), gc.to(dev())])
+        assert l1.item() == l2.item() and torch.isfinite(ld.grad).all()
 
 
 def test_category_out_of_range_poisons_the_loss():
-    """The reference raises IndexError for a category >= C (Vision.py:1593); the kernel cannot raise, so the returned loss
-    is NaN (loud) and the next call is clean again."""
+    """The reference raises IndexError for a category >= C (Vision.py:1593); the fused kernel cannot raise, so the returned
+    loss is NaN (loud) and the next call is clean again."""
     from neuralnetworklibrary_b200.vision import SSD_loss
     H, W, C, B, M = 96, 128, 8, 2, 4
     anchors, an = anchors_for(H, W), orc.anchors(H, W)
     gb, gc = syn.make_targets(B, M, H, W, C, seed=621)
     clas, reg = syn.make_train_activations(B, an.shape[0], C, seed=621)
+    from neuralnetworklibrary_b200 import _lib
     bad = gc.clone()
     bad[0, 0] = C
-    with torch.no_grad():
+    with _lib.option("step_fused", 1), torch.no_grad():
         l_bad = SSD_loss()([anchors, reg.to(dev()), clas.to(dev())], [gb.to(dev()), bad.to(dev())])
         l_ok = SSD_loss()([anchors, reg.to(dev()), clas.to(dev())], [gb.to(dev()), gc.to(dev())])
     assert np.isnan(l_bad.item()) and np.isfinite(l_ok.item())
