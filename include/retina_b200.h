@@ -103,6 +103,14 @@ int rn_stage_targets(const double *boxes, const int64_t *cats, const int32_t *of
 int rn_stage_images(const float *pixels, const int64_t *offsets, const int32_t *dims, int B, int C, int Hp, int Wp,
                     int row_jit, int col_jit, float *out, void *stream);
 
+/* Extension of rn_stage_images for loaders that keep 8-bit images (4x fewer upload bytes): pixels are uint8 HWC, and with
+ * mean / std (host [C], both or neither) out = (float(x) / 255 - mean[c]) / std[c] in fp32, each operation rounded on its
+ * own -- the normalisation the reference's transforms apply on the host (Vision.py section 3) moved behind the upload;
+ * without them out = float(x). */
+int rn_stage_images_u8(const unsigned char *pixels, const int64_t *offsets, const int32_t *dims, int B, int C, int Hp, int Wp,
+                       int row_jit, int col_jit, const float *mean /*host or NULL*/, const float *std /*host or NULL*/,
+                       float *out, void *stream);
+
 /* Workspace for rn_loss (bytes; 256-byte aligned base required). */
 size_t rn_loss_workspace_bytes(int B, int A, int C);
 
@@ -220,6 +228,20 @@ int rn_nms(const float *boxes, const int64_t *classes, const float *scores, int 
            int top_k, int max_keep, int32_t *keep_idx, int32_t *count, void *workspace,
            size_t workspace_bytes, void *stream);
 
+/* nms() for L images in ONE launch (the merge step of ImageLearner.TTA_bbox, Vision.py:2104-2119; also what the drop-in
+ * nms() uses with L = 1): boxes [n_total,4] fp32, classes [n_total] int64, scores [n_total] fp32 are the images' candidates
+ * concatenated, offsets [L+1] int32 (DEVICE) the image boundaries.  Outputs per image, score-descending: out_boxes
+ * [L,max_keep,4], out_classes [L,max_keep] int64, out_scores [L,max_keep], out_idx [L,max_keep] int32 (index inside the
+ * image's own candidates; may be NULL), counts [L] -- one buffer, one device->host copy for the caller.
+ * Optional fused pre-pass (S > 0): the un-transform of Vision.py:2091-2097 per SEGMENT of consecutive boxes (seg_off [S+1]
+ * int32, seg_par [S][5] float64 = col_jit, row_jit, 1/(rand_scale*scale), flip, cols; DEVICE): x -= col_jit, y -= row_jit,
+ * times the factor, then a horizontal flip about cols if flip != 0 -- float64 arithmetic, rounded to float32 once. */
+size_t rn_nms_batch_workspace_bytes(int n_total, int L, int top_k);
+int rn_nms_batch(const float *boxes, const int64_t *classes, const float *scores, const int32_t *offsets, int L, int n_total,
+                 const int32_t *seg_off, const double *seg_par, int S, float max_overlap, int top_k, int max_keep,
+                 float *out_boxes, int64_t *out_classes, float *out_scores, int32_t *out_idx, int32_t *counts,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
 /* The per-image matching of mAP1 (Vision.py:1716-1727) for a whole validation set.
  * Predictions and ground-truth boxes of all images are concatenated: pred_boxes [NP,4] fp32, pred_cls [NP] int32,
  * pred_off [N+1] int32 (image boundaries); targ_boxes [NT,4] fp32, targ_cls [NT] int32, targ_img [NT] int32 (image of
@@ -228,6 +250,16 @@ int rn_nms(const float *boxes, const int64_t *classes, const float *scores, int 
 int rn_map_match(const float *pred_boxes, const int32_t *pred_cls, const int32_t *pred_off, const float *targ_boxes,
                  const int32_t *targ_cls, const int32_t *targ_img, int NT, int NP, const float *thresholds, int T,
                  unsigned char *is_correct, void *stream);
+
+/* The precision/recall integration of mAP1 (Vision.py:1729-1747) for every (threshold, category) pair in one launch
+ * (SURVEY.md section 8f row 4): sort the category's predictions by (score, is_correct) descending, running count of correct
+ * ones times 1/n, running maximum from the right, pairwise sum over the correct positions, divided by the category's number
+ * of ground-truth boxes -- float64, bit for bit what NumPy computes (nan for a category without ground truth).
+ *   pred_scores [NP] fp32; perm [NP] int32 = prediction indices grouped by category, cls_off [C+1] int32 the group boundaries;
+ *   is_correct [T][NP] uint8 from rn_map_match; ntrue [C] int32; table [T][C] float64 (all DEVICE). */
+size_t rn_map_ap_workspace_bytes(int NP, int T);
+int rn_map_ap(const float *pred_scores, const int32_t *perm, const int32_t *cls_off, const unsigned char *is_correct,
+              const int32_t *ntrue, int NP, int C, int T, double *table, void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 # RETINA_B200_LIB overrides the library path (A/B comparisons of builds); the default is the in-tree build.
 LIB_PATH = os.environ.get("RETINA_B200_LIB") or os.path.join(_PKG, "libretina_sm100.so")
-SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_step.cu", "rn_post.cu", "rn_loss_levels.cu"]
+SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_step.cu", "rn_post.cu", "rn_loss_levels.cu", "rn_metrics.cu"]
 BUILD_DIR = os.path.join(_PKG, "csrc", "_build")   # object files (git-ignored); the .so is what travels
 
 NVCC_FLAGS = [
@@ -104,6 +104,8 @@ PROTOTYPES = {
                                   _f32p, _vp]),
     "rn_stage_targets": (C.c_int, [_vp, _i64p, _i32p, _vp, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _i64p, _vp]),
     "rn_stage_images": (C.c_int, [_f32p, _i64p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _vp]),
+    "rn_stage_images_u8": (C.c_int, [_vp, _i64p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _hf32p, _hf32p,
+                                     _f32p, _vp]),
     "rn_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rn_loss": (C.c_int, [_f32p, _f32p, _f32p, _i64p, _i32p, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                           C.c_int, _f64p, C.c_int, _f32p, C.c_double, C.c_double, C.c_double, C.c_int,
@@ -130,6 +132,11 @@ PROTOTYPES = {
                                      C.c_float, C.c_float, C.c_int, C.c_int, _f32p, _i64p, _f32p, _i32p, _i32p, _i32p, _vp,
                                      C.c_size_t, _vp]),
     "rn_map_match": (C.c_int, [_f32p, _i32p, _i32p, _f32p, _i32p, _i32p, C.c_int, C.c_int, _f32p, C.c_int, _vp, _vp]),
+    "rn_nms_batch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "rn_nms_batch": (C.c_int, [_f32p, _i64p, _f32p, _i32p, C.c_int, C.c_int, _i32p, _vp, C.c_int, C.c_float, C.c_int, C.c_int,
+                               _f32p, _i64p, _f32p, _i32p, _i32p, _vp, C.c_size_t, _vp]),
+    "rn_map_ap_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "rn_map_ap": (C.c_int, [_f32p, _i32p, _i32p, _vp, _i32p, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_size_t, _vp]),
     "rn_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "rn_nms": (C.c_int, [_f32p, _i64p, _f32p, C.c_int, C.c_float, C.c_int, C.c_int, _i32p, _i32p, _vp,
                          C.c_size_t, _vp]),

@@ -9,6 +9,8 @@
 // Anchors are generated on the fly (float64 add -> float32, bit-identical to the reference) or read
 // from a caller-supplied table.  The IEEE divide only runs for overlapping pairs.  The work is compute
 // only (reads O(M) bytes per CTA, writes 4 B per anchor).
+#include <string.h>
+
 #include "rn_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -545,23 +547,56 @@ __global__ void rn_stage_targets_kernel(const double *__restrict__ boxes, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Image staging: the pixel half of AspectRatioCollater after its cv2.resize (Vision.py:775-777 jitter placement,
-// :786 HWC -> CHW, :790-796 zero padding of every image to the batch's common 32-multiple size), from one ragged upload.
+// Image staging: the pixel half of AspectRatioCollater after its cv2.resize (Vision.py:775-777 jitter placement, :786 HWC -> CHW,
+// :790-796 zero padding of every image to the batch's common 32-multiple size), from one ragged upload.
 // out[b, c, y, x] = img_b[y - row_jit, x - col_jit, c] inside the image, 0 elsewhere.  Pure data movement: bit exact.
+// One CTA per (output row y, image b): the source row (cols*C consecutive elements) is read with consecutive threads on
+// consecutive addresses into a shared-memory row in pixel-major order, then every channel plane's row is written with
+// 128-bit stores (Wp is a multiple of 32, so each plane row starts 128-byte aligned); the channel-stride shared-memory reads
+// are conflict free for odd C.  First version: one strided 4-byte load per output element (HWC -> CHW uncoalesced).
+// T = float: the reference's format.  T = uint8_t (extension, 4x fewer upload bytes): pixels are 0..255 and
+// out = (float(x) / 255 - mean[c]) / std[c] in fp32, each operation rounded on its own.
+struct RnStageNorm {
+    float mean[8], std[8];
+    int on;
+};
+template <typename T>
 __global__ void __launch_bounds__(256)
-rn_stage_images_kernel(const float *__restrict__ pixels, const int64_t *__restrict__ offsets, const int32_t *__restrict__ dims,
-                       int C, int Hp, int Wp, int row_jit, int col_jit, float *__restrict__ out) {
-    const int b = blockIdx.z, y = blockIdx.y;
+rn_stage_images_kernel(const T *__restrict__ pixels, const int64_t *__restrict__ offsets, const int32_t *__restrict__ dims,
+                       int C, int Hp, int Wp, int row_jit, int col_jit, const __grid_constant__ RnStageNorm norm,
+                       float *__restrict__ out) {
+    extern __shared__ __align__(16) float s_row[];  // [Wp][C]
+    const int b = blockIdx.y, y = blockIdx.x, tid = threadIdx.x;
     const int rows = dims[2 * b], cols = dims[2 * b + 1];
-    const float *src = pixels + offsets[b];
     const int sy = y - row_jit;
     const bool row_in = sy >= 0 && sy < rows;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * Wp; i += gridDim.x * blockDim.x) {
-        const int c = i / Wp, x = i - c * Wp;
-        const int sx = x - col_jit;
+    const int n = C * Wp;
+    const T *src = pixels + offsets[b] + (row_in ? (size_t)sy * cols * C : 0);
+    const int lo = col_jit * C, hi = (col_jit + cols) * C;  // the image's columns in the padded row, in elements
+    for (int i = tid; i < n; i += 256) {
         float v = 0.0f;
-        if (row_in && sx >= 0 && sx < cols) v = __ldg(src + ((size_t)sy * cols + sx) * C + c);
-        out[(((size_t)b * C + c) * Hp + y) * Wp + x] = v;
+        if (row_in && i >= lo && i < hi) {
+            const T raw = __ldg(src + (i - lo));
+            if (sizeof(T) == 1) {
+                v = (float)raw;
+                if (norm.on) {
+                    const int c = i % C;
+                    v = __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), norm.mean[c]), norm.std[c]);
+                }
+            } else {
+                v = (float)raw;
+            }
+        }
+        s_row[i] = v;
+    }
+    __syncthreads();
+    const int W4 = Wp >> 2;
+    for (int c = 0; c < C; ++c) {
+        float4 *dst = reinterpret_cast<float4 *>(out + (((size_t)b * C + c) * Hp + y) * Wp);
+        for (int x4 = tid; x4 < W4; x4 += 256) {
+            const int x = 4 * x4;
+            dst[x4] = make_float4(s_row[x * C + c], s_row[(x + 1) * C + c], s_row[(x + 2) * C + c], s_row[(x + 3) * C + c]);
+        }
     }
 }
 
@@ -673,13 +708,39 @@ extern "C" int rn_stage_targets(const double *boxes, const int64_t *cats, const 
     return rn_check_launch("rn_stage_targets");
 }
 
+template <typename T>
+static int rn_stage_images_impl(const T *pixels, const int64_t *offsets, const int32_t *dims, int B, int C, int Hp, int Wp,
+                                int row_jit, int col_jit, const float *mean, const float *std, float *out, void *stream) {
+    if (B <= 0 || C <= 0 || C > 8 || Hp <= 0 || Wp <= 0 || Hp > 65535 * 32 || B > 65535)
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_stage_images: B=%d C=%d Hp=%d Wp=%d", B, C, Hp, Wp);
+    if (Wp % 4 || (((uintptr_t)out) & 15)) return rn_set_error(RN_ERR_INVALID_ARG, "rn_stage_images: Wp must be a multiple of 4 and out 16-byte aligned");
+    if (!pixels || !offsets || !dims || !out) return rn_set_error(RN_ERR_INVALID_ARG, "rn_stage_images: null pointer");
+    if ((mean == nullptr) != (std == nullptr)) return rn_set_error(RN_ERR_INVALID_ARG, "rn_stage_images: mean and std go together");
+    const size_t smem = sizeof(float) * (size_t)C * (size_t)Wp;
+    if (smem > 200 * 1024) return rn_set_error(RN_ERR_INVALID_ARG, "rn_stage_images: row of %d x %d floats does not fit shared memory", Wp, C);
+    RnStageNorm norm;
+    memset(&norm, 0, sizeof(norm));
+    if (mean) {
+        norm.on = 1;
+        for (int c = 0; c < C; ++c) {
+            norm.mean[c] = mean[c];
+            norm.std[c] = std[c];
+        }
+    }
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(rn_stage_images_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return rn_set_error(RN_ERR_CUDA, "rn_stage_images smem: %s", cudaGetErrorString(e));
+    }
+    rn_stage_images_kernel<T><<<dim3(Hp, B), 256, smem, (cudaStream_t)stream>>>(pixels, offsets, dims, C, Hp, Wp, row_jit, col_jit, norm, out);
+    return rn_check_launch("rn_stage_images");
+}
+
 extern "C" int rn_stage_images(const float *pixels, const int64_t *offsets, const int32_t *dims, int B, int C, int Hp, int Wp,
                                int row_jit, int col_jit, float *out, void *stream) {
-    if (B <= 0 || C <= 0 || Hp <= 0 || Wp <= 0 || Hp > 65535 || B > 65535)
-        return rn_set_error(RN_ERR_INVALID_ARG, "rn_stage_images: B=%d C=%d Hp=%d Wp=%d", B, C, Hp, Wp);
-    if (!pixels || !offsets || !dims || !out) return rn_set_error(RN_ERR_INVALID_ARG, "rn_stage_images: null pointer");
-    const int per_row = C * Wp;
-    dim3 grid((per_row + 255) / 256 > 8 ? 8 : (per_row + 255) / 256, Hp, B);
-    rn_stage_images_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pixels, offsets, dims, C, Hp, Wp, row_jit, col_jit, out);
-    return rn_check_launch("rn_stage_images");
+    return rn_stage_images_impl<float>(pixels, offsets, dims, B, C, Hp, Wp, row_jit, col_jit, nullptr, nullptr, out, stream);
+}
+
+extern "C" int rn_stage_images_u8(const unsigned char *pixels, const int64_t *offsets, const int32_t *dims, int B, int C, int Hp,
+                                  int Wp, int row_jit, int col_jit, const float *mean, const float *std, float *out, void *stream) {
+    return rn_stage_images_impl<unsigned char>(pixels, offsets, dims, B, C, Hp, Wp, row_jit, col_jit, mean, std, out, stream);
 }

@@ -16,6 +16,8 @@
 //                             builds the class-aware suppression bitmask (IoU in strict fp32), one warp
 //                             sweeps it visiting only kept boxes, first max_keep survivors are written.
 // Algorithmic bytes per image: 4*A*(C+4) (clas + reg read); everything after K3a touches O(top_k^2).
+#include <string.h>
+
 #include "rn_common.cuh"
 
 #define RN_SORT_N RN_MAX_TOP_K  // keys that fit the shared-memory sort
@@ -418,6 +420,7 @@ __device__ __forceinline__ int rn_block_excl_scan_1024(int v, int *s_warp /*[32]
 
 __global__ void __launch_bounds__(RN_SEL_THREADS)
 rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t *__restrict__ counts, int cap,
+                      const int32_t *__restrict__ seg_off /* NULL: image b owns keys[b*cap ..); else keys[seg_off[b] .. seg_off[b+1]) */,
                       int top_k, unsigned long long *__restrict__ sel, int32_t *__restrict__ nsel) {
     __shared__ unsigned long long s_keys[RN_SORT_N];
     __shared__ int s_hist[RN_BINS];
@@ -425,10 +428,10 @@ rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t
     __shared__ int s_digit, s_above, s_bincnt, s_n;
 
     const int b = blockIdx.x, tid = threadIdx.x;
-    const unsigned long long *kb = keys + (size_t)b * cap;
     rn_pdl_wait();     // launched with PDL behind the scan kernel
     rn_pdl_trigger();  // the NMS kernel may become resident behind us; it waits for this grid to complete
-    const int n = min(counts[b], cap);
+    const unsigned long long *kb = seg_off ? keys + seg_off[b] : keys + (size_t)b * cap;
+    const int n = seg_off ? seg_off[b + 1] - seg_off[b] : min(counts[b], cap);
     const int K = min(top_k, n);
     if (tid == 0) nsel[b] = K;
     if (K == 0) return;
@@ -525,6 +528,7 @@ struct RnNmsParams {
     // FROM_BOXES = true
     const float4 *boxes_in;
     const int64_t *classes_in;
+    const int32_t *in_off;  // ragged batch (rn_nms_batch): image b owns inputs [in_off[b], in_off[b+1]); NULL: one image
     int top_k, max_keep;
     float max_overlap;
     // outputs (each may be NULL)
@@ -572,8 +576,9 @@ rn_post_nms_kernel(const __grid_constant__ RnNmsParams P, const __grid_constant_
         float4 box;
         int cls;
         if (FROM_BOXES) {
-            box = P.boxes_in[a];
-            cls = (int)P.classes_in[a];
+            const int ga = P.in_off ? P.in_off[b] + a : a;
+            box = P.boxes_in[ga];
+            cls = (int)P.classes_in[ga];
         } else {
             if (pack) {
                 cls = (int)(key & 0xffull);
@@ -640,7 +645,7 @@ rn_post_nms_kernel(const __grid_constant__ RnNmsParams P, const __grid_constant_
     }
 
     if (tid == 0 && P.out_counts) P.out_counts[b] = nk;
-    if (tid == 0 && P.out_ncand) P.out_ncand[b] = P.cand_counts[b];
+    if (tid == 0 && P.out_ncand) P.out_ncand[b] = FROM_BOXES && P.in_off ? P.in_off[b + 1] - P.in_off[b] : P.cand_counts[b];
     for (int t = tid; t < nk; t += nthr) {
         const int i = s_keep[t];
         const unsigned long long key = sel[i];
@@ -681,10 +686,10 @@ extern "C" size_t rn_nms_workspace_bytes(int n, int top_k) {
 }
 
 static int rn_launch_select_nms(bool from_boxes, int B, int cap, RnNmsParams &P, const RnGeom &g, const RnDecode &dec,
-                                unsigned char *ws, const RnPostWs &L, cudaStream_t s) {
+                                unsigned char *ws, const RnPostWs &L, cudaStream_t s, const int32_t *seg_off = nullptr) {
     rn_launch_pdl(rn_post_select_kernel, dim3(B), dim3(RN_SEL_THREADS), 0, s,
                   reinterpret_cast<const unsigned long long *>(ws + L.keys), reinterpret_cast<const int32_t *>(ws + L.counts), cap,
-                  P.top_k, reinterpret_cast<unsigned long long *>(ws + L.sel), reinterpret_cast<int32_t *>(ws + L.nsel));
+                  seg_off, P.top_k, reinterpret_cast<unsigned long long *>(ws + L.sel), reinterpret_cast<int32_t *>(ws + L.nsel));
     int rc = rn_check_launch("rn_post_select");
     if (rc) return rc;
     P.sel = reinterpret_cast<unsigned long long *>(ws + L.sel);
@@ -871,6 +876,119 @@ extern "C" int rn_nms(const float *boxes, const int64_t *classes, const float *s
     P.top_k = top_k; P.max_keep = max_keep; P.max_overlap = max_overlap;
     P.out_idx = keep_idx; P.out_counts = count;
     return rn_launch_select_nms(true, 1, n, P, g, dec, ws, L, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// nms() for MANY images in one launch (the merge step of ImageLearner.TTA_bbox, Vision.py:2104-2119, calls nms once per
+// image on the concatenated predictions of its five passes): the images' boxes / classes / scores are concatenated, offsets
+// [L+1] gives the image boundaries.  Optionally the boxes are first mapped back to the original image -- the un-transform of
+// Vision.py:2091-2097 -- per SEGMENT (= the predictions of one pass for one image): x -= col_jit, y -= row_jit, all * factor,
+// then a horizontal flip about `cols`; float64 like NumPy's arithmetic on a float32 array and int64 / float64 scalars, rounded
+// to float32 once (the TEN() of Vision.py:2112).
+// ------------------------------------------------------------------------------------------------
+__global__ void rn_nms_batch_keys_kernel(const float *__restrict__ scores, const int32_t *__restrict__ offsets, int L, int n,
+                                         unsigned long long *__restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = L;  // image of element i: largest b with offsets[b] <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (offsets[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    keys[i] = rn_make_key(scores[i], i - offsets[lo], 0, false);
+}
+
+__global__ void rn_tta_untransform_kernel(const float4 *__restrict__ boxes, const int32_t *__restrict__ seg_off, int S,
+                                          const double *__restrict__ seg_par /*[S][5]: col_jit, row_jit, factor, flip, cols*/,
+                                          int n, float4 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = S;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (seg_off[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    const double *p = seg_par + 5 * (size_t)lo;
+    const float4 b = boxes[i];
+    double x1 = __dmul_rn(p[2], __dsub_rn((double)b.x, p[0]));  // (1/(rand_scale*scale)) * (x - col_jit), Vision.py:2093-2094
+    double y1 = __dmul_rn(p[2], __dsub_rn((double)b.y, p[1]));
+    double x2 = __dmul_rn(p[2], __dsub_rn((double)b.z, p[0]));
+    double y2 = __dmul_rn(p[2], __dsub_rn((double)b.w, p[1]));
+    if (p[3] != 0.0) {  // Vision.py:2095-2096
+        const double nx1 = __dsub_rn(p[4], x2), nx2 = __dsub_rn(p[4], x1);
+        x1 = nx1;
+        x2 = nx2;
+    }
+    out[i] = make_float4(__double2float_rn(x1), __double2float_rn(y1), __double2float_rn(x2), __double2float_rn(y2));
+}
+
+struct RnNmsBatchWs {
+    size_t post, boxes, total;
+};
+static RnNmsBatchWs rn_nms_batch_layout(int n_total, int L, int top_k) {
+    RnNmsBatchWs w;
+    // keys are stored ragged (n_total of them); the select / nms scratch is sized per image
+    RnPostWs p = rn_post_layout(L, 1, top_k);
+    w.post = 0;
+    size_t o = p.total + rn_up256(sizeof(unsigned long long) * (size_t)(n_total > 0 ? n_total : 1));
+    w.boxes = o; o += rn_up256(sizeof(float4) * (size_t)(n_total > 0 ? n_total : 1));
+    w.total = o;
+    return w;
+}
+
+extern "C" size_t rn_nms_batch_workspace_bytes(int n_total, int L, int top_k) {
+    if (L <= 0 || top_k <= 0) return 256;
+    return rn_nms_batch_layout(n_total, L, top_k).total;
+}
+
+extern "C" int rn_nms_batch(const float *boxes, const int64_t *classes, const float *scores, const int32_t *offsets, int L,
+                            int n_total, const int32_t *seg_off, const double *seg_par, int S, float max_overlap, int top_k,
+                            int max_keep, float *out_boxes, int64_t *out_classes, float *out_scores, int32_t *out_idx,
+                            int32_t *counts, void *workspace, size_t workspace_bytes, void *stream) {
+    if (L <= 0 || n_total < 0 || S < 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms_batch: L=%d n_total=%d S=%d", L, n_total, S);
+    if (!offsets || !counts || !out_boxes || !out_classes || !out_scores) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms_batch: null pointer");
+    if (n_total > 0 && (!boxes || !classes || !scores)) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms_batch: null input");
+    if (S > 0 && (!seg_off || !seg_par)) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms_batch: null segment table");
+    if ((((uintptr_t)boxes) | ((uintptr_t)out_boxes)) & 15) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms_batch: boxes must be 16-byte aligned");
+    if (top_k < 1 || top_k > RN_MAX_TOP_K) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms_batch: top_k=%d outside [1,%d]", top_k, RN_MAX_TOP_K);
+    if (max_keep < 1 || max_keep > top_k) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms_batch: max_keep=%d outside [1,top_k=%d]", max_keep, top_k);
+    if (L > 65535) return rn_set_error(RN_ERR_INVALID_ARG, "rn_nms_batch: L=%d too large", L);
+    const RnNmsBatchWs W = rn_nms_batch_layout(n_total, L, top_k);
+    if (!workspace || workspace_bytes < W.total || (((uintptr_t)workspace) & 255))
+        return rn_set_error(RN_ERR_WORKSPACE, "rn_nms_batch: workspace needs %zu bytes, 256-byte aligned", W.total);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+    const RnPostWs P0 = rn_post_layout(L, 1, top_k);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(ws + P0.total);
+    const float4 *in_boxes = reinterpret_cast<const float4 *>(boxes);
+    if (n_total > 0) {
+        if (S > 0) {
+            float4 *tb = reinterpret_cast<float4 *>(ws + W.boxes);
+            rn_tta_untransform_kernel<<<(n_total + 255) / 256, 256, 0, s>>>(in_boxes, seg_off, S, seg_par, n_total, tb);
+            in_boxes = tb;
+        }
+        rn_nms_batch_keys_kernel<<<(n_total + 255) / 256, 256, 0, s>>>(scores, offsets, L, n_total, keys);
+        int rc = rn_check_launch("rn_nms_batch keys");
+        if (rc) return rc;
+    }
+    RnGeom g;
+    memset(&g, 0, sizeof(g));
+    RnDecode dec;
+    memset(&dec, 0, sizeof(dec));
+    RnNmsParams P;
+    memset(&P, 0, sizeof(P));
+    P.boxes_in = in_boxes;
+    P.classes_in = classes;
+    P.in_off = offsets;
+    P.top_k = top_k; P.max_keep = max_keep; P.max_overlap = max_overlap;
+    P.out_boxes = reinterpret_cast<float4 *>(out_boxes); P.out_classes = out_classes; P.out_scores = out_scores;
+    P.out_idx = out_idx; P.out_counts = counts;
+    // select / nms read their key segments through `offsets`; their scratch (sel, nsel) lives in the per-image layout
+    RnPostWs Lw = P0;
+    Lw.keys = P0.total;  // the ragged key array
+    return rn_launch_select_nms(true, L, 0, P, g, dec, ws, Lw, s, offsets);
 }
 
 // ------------------------------------------------------------------------------------------------

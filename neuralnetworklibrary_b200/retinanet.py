@@ -190,13 +190,51 @@ def _host_stages(boxes, classes, scores, rel_thresh, inc, dup):
     return keep
 
 
+def _nms_layout(L, K):
+    # boxes | classes | scores | idx | counts  (byte offsets into one buffer; boxes 16-byte, classes 8-byte aligned)
+    o_box, o_cls, o_sc, o_idx = 0, 16 * L * K, 24 * L * K, 28 * L * K
+    o_cnt = 32 * L * K
+    return o_box, o_cls, o_sc, o_idx, o_cnt, o_cnt + 4 * L
+
+
+def nms_batch_device(boxes, classes, scores, offsets, max_overlap=0.5, top_k=1000, max_keep=20, seg_off=None, seg_par=None):
+    """rn_nms_batch on device tensors: boxes [n,4] f32, classes [n] i64, scores [n] f32 are the candidates of L images
+    concatenated, offsets [L+1] i32 the image boundaries (optionally the TTA un-transform table seg_off [S+1] i32 / seg_par
+    [S,5] f64, see include/retina_b200.h).  One launch sequence, no host synchronisation; returns (uint8 device buffer, K)
+    laid out by _nms_layout -- decode it after ONE .cpu()."""
+    lib = _lib.load()
+    dev = boxes.device
+    L, n = int(offsets.shape[0]) - 1, int(scores.shape[0])
+    S = 0 if seg_off is None else int(seg_off.shape[0]) - 1
+    o_box, o_cls, o_sc, o_idx, o_cnt, total = _nms_layout(L, max_keep)
+    with torch.cuda.device(dev):
+        buf = torch.empty(total, dtype=torch.uint8, device=dev)
+        ws = _ws.get(lib.rn_nms_batch_workspace_bytes(n, L, top_k), dev)
+        p = buf.data_ptr()
+        _lib.check(lib.rn_nms_batch(_lib.ptr(boxes), _lib.ptr(classes), _lib.ptr(scores), _lib.ptr(offsets), L, n,
+                                    _lib.ptr(seg_off), _lib.ptr(seg_par), S, float(max_overlap), int(top_k), int(max_keep),
+                                    C.c_void_p(p + o_box), C.c_void_p(p + o_cls), C.c_void_p(p + o_sc), C.c_void_p(p + o_idx),
+                                    C.c_void_p(p + o_cnt), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+    return buf, max_keep
+
+
+def decode_nms_buffer(host, L, K):
+    """Views into the host copy of nms_batch_device's buffer: boxes [L,K,4] f32, classes [L,K] i64, scores [L,K] f32,
+    idx [L,K] i32, counts [L] i32."""
+    o_box, o_cls, o_sc, o_idx, o_cnt, total = _nms_layout(L, K)
+    return (host[o_box:o_cls].view(np.float32).reshape(L, K, 4), host[o_cls:o_sc].view(np.int64).reshape(L, K),
+            host[o_sc:o_idx].view(np.float32).reshape(L, K), host[o_idx:o_cnt].view(np.int32).reshape(L, K),
+            host[o_cnt:total].view(np.int32))
+
+
 def nms(pred_boxes, pred_classes, conf_scores, max_overlap=0.5, rel_thresh=None,
         top_k=1000, max_boxes=20, dup=None, inc=None, print_it=False):
     """Non-maximum suppression for one image (reference retinanet.py:523-711), same arguments and
     return value: three lists (np.ndarray[4] float32, np.int64, np.float32), score-descending.
 
-    Sort, top_k and the class-aware greedy suppression run on the GPU (rn_nms: radix select + bitonic
-    sort + bitmask sweep); score ties are ordered by input position (the reference's sort is unstable)."""
+    Sort, top_k and the class-aware greedy suppression run on the GPU (rn_nms_batch with one image: radix select + bitonic
+    sort + bitmask sweep, survivors gathered on the device) and come back in ONE device->host copy; score ties are
+    ordered by input position (the reference's sort is unstable)."""
     if len(pred_boxes) == 0:
         return [], [], []
     boxes = torch.as_tensor(pred_boxes)
@@ -214,20 +252,11 @@ def nms(pred_boxes, pred_classes, conf_scores, max_overlap=0.5, rel_thresh=None,
         raise ValueError("top_k > %d is not supported" % _lib.MAX_TOP_K)
     extra = bool(rel_thresh) or bool(inc) or bool(dup)
     max_keep = top_k if extra else max(1, min(int(max_boxes), top_k))
-
-    lib = _lib.load()
-    with torch.cuda.device(dev):
-        nbytes = lib.rn_nms_workspace_bytes(n, top_k)
-        ws = _ws.get(nbytes, dev)
-        out = torch.empty(max_keep + 1, dtype=torch.int32, device=dev)   # [count | keep_idx...]
-        _lib.check(lib.rn_nms(_lib.ptr(boxes), _lib.ptr(classes), _lib.ptr(scores), n, float(max_overlap), top_k,
-                              max_keep, C.c_void_p(out.data_ptr() + 4), _lib.ptr(out), _lib.ptr(ws), ws.numel(),
-                              _lib.stream_ptr(dev)))
-        host = out.cpu().numpy()
-        keep = torch.from_numpy(host[1:1 + int(host[0])].astype(np.int64)).to(dev)
-        kb = boxes.index_select(0, keep).cpu().numpy()
-        kc = classes.index_select(0, keep).cpu().numpy()
-        ks = scores.index_select(0, keep).cpu().numpy()
+    offsets = torch.tensor([0, n], dtype=torch.int32, device=dev)
+    buf, K = nms_batch_device(boxes, classes, scores, offsets, max_overlap, top_k, max_keep)
+    kb, kc, ks, _, cnt = decode_nms_buffer(buf.cpu().numpy(), 1, K)   # the one device->host copy (and synchronisation)
+    k = int(cnt[0])
+    kb, kc, ks = kb[0, :k], kc[0, :k], ks[0, :k]
     if print_it:
         print('after non-max-supress')
         print(len(kb), len(kc), len(ks))

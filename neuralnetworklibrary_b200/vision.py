@@ -549,12 +549,16 @@ def stage_targets(bboxes, cats, scales, rand_scale=1.0, row_jit=0, col_jit=0, de
     return [out_boxes, out_cats]
 
 
-def stage_images(images, row_jit=0, col_jit=0, device=None):
+def stage_images(images, row_jit=0, col_jit=0, device=None, mean=None, std=None):
     """Device-side version of the pixel half of AspectRatioCollater after its cv2.resize (reference Vision.py:775-777,
     :786, :790-796): every (already resized) H x W x C image is placed at (row_jit, col_jit), transposed to C x H x W and
     zero-padded to the batch's common size, height and width rounded up to multiples of 32 -- from ONE pinned, ragged
     host->device upload and one kernel instead of two padded host arrays and a transpose per batch.  Returns a float32
-    tensor [bs, C, H, W] on the device (what the reference hands to to_cuda)."""
+    tensor [bs, C, H, W] on the device (what the reference hands to to_cuda).
+
+    Extension: uint8 images (0..255) are uploaded as bytes (4x less PCIe traffic) and converted on the device; with
+    `mean` / `std` (per channel) the result is (x / 255 - mean) / std in float32, the normalisation the reference's
+    transforms apply on the host before the collater."""
     lib = _lib.load()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     B = len(images)
@@ -564,6 +568,11 @@ def stage_images(images, row_jit=0, col_jit=0, device=None):
     if any(len(s) != 3 or s[2] != shapes[0][2] for s in shapes):
         raise ValueError("images must be H x W x C arrays with the same number of channels")
     Cn = shapes[0][2]
+    as_bytes = all(np.asarray(im).dtype == np.uint8 for im in images)
+    if (mean is None) != (std is None):
+        raise ValueError("mean and std go together")
+    if mean is not None and not as_bytes:
+        raise ValueError("mean / std apply to uint8 images only (float images arrive normalised, as in the reference)")
     row_jit, col_jit = int(row_jit), int(col_jit)
     Hp = int(32 * np.ceil(max(s[0] + row_jit for s in shapes) / 32))     # Vision.py:790-792
     Wp = int(32 * np.ceil(max(s[1] + col_jit for s in shapes) / 32))
@@ -571,14 +580,15 @@ def stage_images(images, row_jit=0, col_jit=0, device=None):
     offsets = np.zeros(B, dtype=np.int64)
     offsets[1:] = np.cumsum(sizes)[:-1]
     total = int(sum(sizes))
-    # one pinned staging buffer: pixels f32 [total] | offsets i64 [B] | dims i32 [B,2]
-    npx, nof, ndm = 4 * total, 8 * B, 8 * B
+    # one pinned staging buffer: pixels (f32 or u8) [total] | offsets i64 [B] | dims i32 [B,2]
+    esz = 1 if as_bytes else 4
+    npx, nof, ndm = esz * total, 8 * B, 8 * B
     pad = (-npx) % 8
     host = torch.empty(npx + pad + nof + ndm, dtype=torch.uint8, pin_memory=True)
     hv = host.numpy()
-    px = hv[:npx].view(np.float32)
+    px = hv[:npx] if as_bytes else hv[:npx].view(np.float32)
     for i, im in enumerate(images):
-        px[offsets[i]:offsets[i] + sizes[i]] = np.asarray(im).astype(np.float32, copy=False).reshape(-1)   # Vision.py:776
+        px[offsets[i]:offsets[i] + sizes[i]] = np.asarray(im).astype(np.uint8 if as_bytes else np.float32, copy=False).reshape(-1)   # Vision.py:776
     hv[npx + pad:npx + pad + nof].view(np.int64)[:] = offsets
     hv[npx + pad + nof:].view(np.int32)[:] = np.array([[s[0], s[1]] for s in shapes], dtype=np.int32).reshape(-1)
     with torch.cuda.device(device):
@@ -586,28 +596,101 @@ def stage_images(images, row_jit=0, col_jit=0, device=None):
         out = torch.empty((B, Cn, Hp, Wp), dtype=torch.float32, device=device)
         p = dev_buf.data_ptr()
         import ctypes as C
-        _lib.check(lib.rn_stage_images(C.c_void_p(p), C.c_void_p(p + npx + pad), C.c_void_p(p + npx + pad + nof), B, Cn, Hp, Wp,
-                                       row_jit, col_jit, _lib.ptr(out), _lib.stream_ptr(device)))
+        if as_bytes:
+            m32 = s32 = None
+            if mean is not None:
+                m32 = np.ascontiguousarray(mean, dtype=np.float32).reshape(Cn)
+                s32 = np.ascontiguousarray(std, dtype=np.float32).reshape(Cn)
+            _lib.check(lib.rn_stage_images_u8(C.c_void_p(p), C.c_void_p(p + npx + pad), C.c_void_p(p + npx + pad + nof), B, Cn, Hp, Wp,
+                                              row_jit, col_jit, None if m32 is None else m32.ctypes.data_as(_lib._hf32p),
+                                              None if s32 is None else s32.ctypes.data_as(_lib._hf32p), _lib.ptr(out),
+                                              _lib.stream_ptr(device)))
+        else:
+            _lib.check(lib.rn_stage_images(C.c_void_p(p), C.c_void_p(p + npx + pad), C.c_void_p(p + npx + pad + nof), B, Cn, Hp, Wp,
+                                           row_jit, col_jit, _lib.ptr(out), _lib.stream_ptr(device)))
         dev_buf.record_stream(torch.cuda.current_stream(device))
     return out
 
 
-def merge_tta_predictions(passes, max_overlap=0.5, rel_thresh=None, top_k=1000, max_boxes=20, dup=None, inc=None):
-    """The merge step of ImageLearner.TTA_bbox (reference Vision.py:2104-2119): `passes` is a list (one entry per
-    augmentation pass) of per-image [boxes, classes, scores] lists already mapped back to the original image; the
-    passes' predictions of each image are concatenated and nms() (GPU) is applied to the union."""
-    from .retinanet import nms
+def merge_tta_predictions(passes, max_overlap=0.5, rel_thresh=None, top_k=1000, max_boxes=20, dup=None, inc=None,
+                          transforms=None, device=None):
+    """The merge step of ImageLearner.TTA_bbox (reference Vision.py:2104-2119) for ALL images in one launch: `passes` is a
+    list (one entry per augmentation pass) of per-image [boxes, classes, scores] lists; the passes' predictions of each
+    image are concatenated and nms is applied to the union -- rn_nms_batch: one ragged pinned upload, one launch
+    sequence, one device->host copy, instead of one nms() call (and several copies) per image.
+
+    transforms: None when the boxes are already mapped back to the original image (what TTA_bbox's loop does on the host,
+    Vision.py:2091-2097); else transforms[i][l] = dict(row_jit, col_jit, rand_scale, scale, flip, cols) for pass i, image l
+    and the un-transform runs on the device, fused in front of the NMS (float64 arithmetic rounded to float32 once, like
+    NumPy >= 2 evaluates those lines for int64 jitter values)."""
+    from .retinanet import _host_stages, decode_nms_buffer, nms_batch_device
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     L = len(passes[0])
-    merged = []
+    counts = np.zeros(L, np.int64)
+    seg_counts, seg_par = [], []
     for l in range(L):
-        boxes, classes, scores = [], [], []
+        for i, p in enumerate(passes):
+            k = len(p[l][0])
+            counts[l] += k
+            if transforms is not None:
+                t = transforms[i][l]
+                seg_counts.append(k)
+                seg_par.append([float(t["col_jit"]), float(t["row_jit"]), 1 / (float(t["rand_scale"]) * float(t["scale"])),
+                                1.0 if (i > 0 and int(t["flip"]) == 1) else 0.0, float(t["cols"])])   # Vision.py:2095: i>0 and flip==1
+    n = int(counts.sum())
+    if n == 0:
+        return [[[], [], []] for _ in range(L)]
+    top_k = int(top_k)
+    if top_k < 1:
+        return [[[], [], []] for _ in range(L)]
+    extra = bool(rel_thresh) or bool(inc) or bool(dup)
+    max_keep = top_k if extra else max(1, min(int(max_boxes), top_k))
+    S = len(seg_counts)
+    # one pinned staging buffer: boxes f32 [n,4] | classes i64 [n] | scores f32 [n] | offsets i32 [L+1] | seg_off i32 [S+1] | seg_par f64 [S,5]
+    nb, nc, ns, no = 16 * n, 8 * n, 4 * n, 4 * (L + 1)
+    nso, nsp = 4 * (S + 1), 40 * S
+    pad1 = (-(nb + nc + ns + no + nso)) % 8
+    host = torch.empty(nb + nc + ns + no + nso + pad1 + nsp + 16, dtype=torch.uint8, pin_memory=True)
+    hv = host.numpy()
+    hb = hv[:nb].view(np.float32).reshape(n, 4)
+    hc = hv[nb:nb + nc].view(np.int64)
+    hs = hv[nb + nc:nb + nc + ns].view(np.float32)
+    pos = 0
+    for l in range(L):
         for p in passes:
-            boxes += list(p[l][0])
-            classes += list(p[l][1])
-            scores += list(p[l][2])
-        if len(boxes) == 0:
-            merged.append([[], [], []])
-            continue
-        merged.append(list(nms(TEN(boxes), TEN([int(c) for c in classes]), TEN([float(v) for v in scores]), max_overlap,
-                               rel_thresh, top_k, max_boxes, dup, inc)))
+            k = len(p[l][0])
+            if k:
+                hb[pos:pos + k] = np.asarray(p[l][0], dtype=np.float32).reshape(k, 4)
+                hc[pos:pos + k] = np.asarray([int(c) for c in p[l][1]], dtype=np.int64)
+                hs[pos:pos + k] = np.asarray(p[l][2], dtype=np.float32)
+                pos += k
+    offs = np.zeros(L + 1, np.int32)
+    offs[1:] = np.cumsum(counts)
+    hv[nb + nc + ns:nb + nc + ns + no].view(np.int32)[:] = offs
+    o_so = nb + nc + ns + no
+    o_sp = o_so + nso + pad1
+    if S:
+        so = np.zeros(S + 1, np.int32)
+        so[1:] = np.cumsum(seg_counts)
+        hv[o_so:o_so + nso].view(np.int32)[:] = so
+        hv[o_sp:o_sp + nsp].view(np.float64)[:] = np.asarray(seg_par, np.float64).reshape(-1)
+    with torch.cuda.device(device):
+        d = host.to(device, non_blocking=True)
+        boxes = d[:nb].view(torch.float32).view(n, 4)
+        classes = d[nb:nb + nc].view(torch.int64)
+        scores = d[nb + nc:nb + nc + ns].view(torch.float32)
+        offsets = d[nb + nc + ns:nb + nc + ns + no].view(torch.int32)
+        seg_off = d[o_so:o_so + nso].view(torch.int32) if S else None
+        seg_pr = d[o_sp:o_sp + nsp].view(torch.float64) if S else None
+        buf, K = nms_batch_device(boxes, classes, scores, offsets, max_overlap, top_k, max_keep, seg_off, seg_pr)
+        kb, kc, ks, _, cnt = decode_nms_buffer(buf.cpu().numpy(), L, K)   # the one device->host copy
+    merged = []
+    m = max(int(max_boxes), 0)
+    for l in range(L):
+        k = int(cnt[l])
+        b, c, s = kb[l, :k], kc[l, :k], ks[l, :k]
+        if k and extra:
+            sel = _host_stages(b, c, s, rel_thresh, inc, dup)
+            b, c, s = b[sel], c[sel], s[sel]
+        merged.append([list(b[:m]), list(c[:m]), list(s[:m])])
     return merged

@@ -106,3 +106,64 @@ def test_kernel_matches_reference_collater_images(golden_dir):
     assert np.array_equal(out.cpu().numpy(), orc.stage_images(imgs, 7, 13))
     with pytest.raises(ValueError):
         stage_images([])
+
+
+@pytest.mark.gpu
+def test_stage_images_uint8_upload_and_normalisation():
+    """Extension: 8-bit images are uploaded as bytes and converted (optionally normalised) on the device."""
+    from neuralnetworklibrary_b200.vision import stage_images
+    rng = np.random.RandomState(11)
+    imgs = [rng.randint(0, 256, size=(int(rng.randint(40, 90)), int(rng.randint(50, 130)), 3)).astype(np.uint8) for _ in range(3)]
+    plain = stage_images(imgs, 3, 5)
+    assert np.array_equal(plain.cpu().numpy(), orc.stage_images([im.astype(np.float32) for im in imgs], 3, 5))
+    mean, std = np.array([0.485, 0.456, 0.406], np.float32), np.array([0.229, 0.224, 0.225], np.float32)
+    got = stage_images(imgs, 3, 5, mean=mean, std=std).cpu().numpy()
+    want = orc.stage_images([((im.astype(np.float32) / np.float32(255)) - mean) / std for im in imgs], 3, 5)
+    # padding stays exactly 0, pixels equal the float32 restatement bit for bit
+    assert np.array_equal(got, want)
+    with pytest.raises(ValueError):
+        stage_images([im.astype(np.float32) for im in imgs], mean=mean, std=std)
+
+
+@pytest.mark.gpu
+def test_merge_tta_predictions_device_untransform():
+    """merge_tta_predictions(transforms=...) = the reference's host un-transform (Vision.py:2091-2097, float64 like NumPy >= 2
+    evaluates it for int64 jitter values, rounded to float32 by TEN) followed by the merge without transforms."""
+    from neuralnetworklibrary_b200.vision import merge_tta_predictions
+    rng = np.random.RandomState(7)
+    L, NP = 4, 5
+    passes, transforms, host_passes = [], [], []
+    for i in range(NP):
+        per_image, per_tf, per_host = [], [], []
+        for l in range(L):
+            n = int(rng.randint(0, 15)) if not (l == 2 and i < 3) else 0
+            xy = rng.uniform(0, 300, (n, 2))
+            wh = rng.uniform(10, 120, (n, 2))
+            boxes = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+            classes = list(rng.randint(0, 3, n).astype(np.int64))
+            scores = list(rng.uniform(0.05, 1, n).astype(np.float32))
+            tf = dict(row_jit=np.int64(rng.randint(0, 9)), col_jit=np.int64(rng.randint(0, 9)), rand_scale=np.float64(rng.uniform(0.9, 1.1)),
+                      scale=float(rng.uniform(0.4, 1.2)), flip=int(rng.randint(0, 2)), cols=int(rng.randint(300, 700)))
+            per_image.append([list(boxes), classes, scores])
+            per_tf.append(tf)
+            hb = []
+            if n:   # the reference's lines, on the host
+                b = np.array(list(boxes))
+                b = np.array([b[:, 0] - tf["col_jit"], b[:, 1] - tf["row_jit"], b[:, 2] - tf["col_jit"], b[:, 3] - tf["row_jit"]]).T
+                b = (1 / (tf["rand_scale"] * tf["scale"])) * b
+                if i > 0 and tf["flip"] == 1:
+                    b = np.array([tf["cols"] - b[:, 2], b[:, 1], tf["cols"] - b[:, 0], b[:, 3]]).T
+                hb = list(b.astype(np.float32))
+            per_host.append([hb, classes, scores])
+        passes.append(per_image)
+        transforms.append(per_tf)
+        host_passes.append(per_host)
+    for kw in (dict(max_boxes=50), dict(max_boxes=50, rel_thresh=[0.2, 0.5])):
+        got = merge_tta_predictions(passes, transforms=transforms, **kw)
+        want = merge_tta_predictions(host_passes, **kw)
+        assert len(got) == len(want) == L
+        for g_, w_ in zip(got, want):
+            assert len(g_[0]) == len(w_[0])
+            if len(g_[0]):
+                assert np.array_equal(np.stack(g_[0]).view(np.uint32), np.stack(w_[0]).view(np.uint32))
+                assert np.array_equal(np.array(g_[1]), np.array(w_[1])) and np.array_equal(np.array(g_[2]), np.array(w_[2]))
