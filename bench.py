@@ -288,7 +288,7 @@ def time_loss_eager(anchors, sets, steps, warmup, device):
 
     def timed_rn_loss(clas, reg, gtb, gtc, B, A, C, M, H, W, base, K, table, pos, neg, alpha, gamma, beta, Bg, logits, dclas, dreg,
                       probs, out3, npos, matches, state, state_n, ws, ws_n, stream):
-        if logits or lib.rn_get_option(b"step_fused") > 0:
+        if logits or lib.rn_get_option(b"step_fused") > 0 or lib.rn_get_option(b"step_bytemap") > 0:
             return orig(clas, reg, gtb, gtc, B, A, C, M, H, W, base, K, table, pos, neg, alpha, gamma, beta, Bg, logits, dclas,
                         dreg, probs, out3, npos, matches, state, state_n, ws, ws_n, stream)
         key = (B, A, C)
@@ -457,6 +457,116 @@ def time_postproc_levels(cfg, B, steps, warmup, device, from_logits, seed=1011):
     except Exception:
         pass
     return dev_ms, lay_ms, int(out["n_candidates"].mean()), int(out["counts"].sum())
+
+
+def time_aux_kernels(device, peak):
+    """Device time, algorithmic bytes and HBM fraction of the kernels around the two hot paths (SURVEY.md section 8f rows
+    2-4): rn_max_overlaps, rn_stage_targets, rn_stage_images (fp32 and uint8 upload), rn_nms_batch (TTA merge) and the
+    mAP pair rn_map_match + rn_map_ap.  Most are latency-bound (a few microseconds); the fraction says so."""
+    import numpy as np
+    import torch
+
+    from neuralnetworklibrary_b200 import metrics
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator
+    from neuralnetworklibrary_b200.vision import ComputeMaxOverlaps, merge_tta_predictions, stage_images, stage_targets
+    from tests import synth as syn
+
+    out = {}
+
+    def timed(fn, reps=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(device)
+        return e0.elapsed_time(e1) / reps
+
+    def entry(ms, nbytes, note):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        return {"ms": round(ms, 4), "algorithmic_bytes": int(nbytes), "gb_per_s": round(gbs, 1), "hbm_frac": round(gbs / peak, 4), "note": note}
+
+    H, W, C, M, B = COCO["H"], COCO["W"], COCO["C"], COCO["M"], 16
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=device))
+    gb, gc = syn.make_targets(B, M, H, W, C, seed=21)
+    gbd, gcd = gb.to(device), gc.to(device)
+    lib = __import__("neuralnetworklibrary_b200._lib", fromlist=["x"])
+    L = lib.load()
+    mo = torch.empty((B, M), dtype=torch.float32, device=device)
+    from neuralnetworklibrary_b200.retinanet import anchor_args
+    Hh, Ww, base, K, table, A = anchor_args(anchors)
+    ms = timed(lambda: lib.check(L.rn_max_overlaps(lib.ptr(gbd), lib.ptr(gcd), B, M, Hh, Ww, base, K, table, A, lib.ptr(mo), lib.stream_ptr(device))))
+    out["rn_max_overlaps"] = entry(ms, B * M * 24, "compute bound: B*A*M IoU evaluations (%.0f M) on generated anchors, 24 B per box in/out" % (B * A * M / 1e6))
+
+    rng = np.random.RandomState(4)
+    boxes = [rng.uniform(0, 500, size=(int(rng.randint(1, M + 1)), 4)) for _ in range(B)]
+    cats = [rng.randint(0, C, size=len(b)) for b in boxes]
+    scales = rng.uniform(0.5, 1.5, size=B)
+    ms = timed(lambda: stage_targets(boxes, cats, scales, 1.05, 3, 5, device=device))
+    out["stage_targets (host packing + H2D + rn_stage_targets)"] = entry(ms, B * M * 24 + sum(len(b) for b in boxes) * 40, "wall-clock dominated by the host packing; the kernel is one launch of B*M threads")
+
+    imgs = [rng.rand(int(rng.randint(700, 801)), int(rng.randint(1100, 1334)), 3).astype(np.float32) for _ in range(8)]
+    px = sum(im.size for im in imgs)
+    res = stage_images(imgs, 4, 6, device=device)
+    obytes = res.numel() * 4
+
+    def kernel_only(u8):
+        # the kernel alone on device-resident pixels (the public call also packs and uploads)
+        import ctypes as Cc
+        flat = torch.from_numpy(np.concatenate([(im * 255).astype(np.uint8).reshape(-1) if u8 else im.reshape(-1) for im in imgs])).to(device)
+        offs = np.zeros(len(imgs), np.int64)
+        offs[1:] = np.cumsum([im.size for im in imgs])[:-1]
+        d_off = torch.from_numpy(offs).to(device)
+        d_dim = torch.from_numpy(np.array([[im.shape[0], im.shape[1]] for im in imgs], np.int32)).to(device)
+        o = torch.empty_like(res)
+        if u8:
+            f = lambda: lib.check(L.rn_stage_images_u8(lib.ptr(flat), lib.ptr(d_off), lib.ptr(d_dim), len(imgs), 3, res.shape[2], res.shape[3], 4, 6, None, None, lib.ptr(o), lib.stream_ptr(device)))
+        else:
+            f = lambda: lib.check(L.rn_stage_images(lib.ptr(flat), lib.ptr(d_off), lib.ptr(d_dim), len(imgs), 3, res.shape[2], res.shape[3], 4, 6, lib.ptr(o), lib.stream_ptr(device)))
+        return timed(f)
+
+    out["rn_stage_images fp32 (kernel, 8 COCO-sized images)"] = entry(kernel_only(False), px * 4 + obytes, "read HWC fp32 + write padded CHW fp32")
+    out["rn_stage_images uint8 (kernel, 8 COCO-sized images)"] = entry(kernel_only(True), px + obytes, "read HWC uint8 (4x fewer upload bytes) + write padded CHW fp32")
+    ms_pub32 = timed(lambda: stage_images(imgs, 4, 6, device=device), reps=3, warm=1)
+    imgs8 = [(im * 255).astype(np.uint8) for im in imgs]
+    ms_pub8 = timed(lambda: stage_images(imgs8, 4, 6, device=device), reps=3, warm=1)
+    out["stage_images public call (pack + H2D + kernel)"] = {"fp32_ms": round(ms_pub32, 3), "uint8_ms": round(ms_pub8, 3), "h2d_bytes_fp32": px * 4, "h2d_bytes_uint8": px}
+
+    # TTA merge: 64 images x 5 passes x ~20 boxes
+    passes = []
+    for p in range(5):
+        per = []
+        for l in range(64):
+            n = int(rng.randint(5, 21))
+            xy = rng.uniform(0, 600, (n, 2)); wh = rng.uniform(20, 200, (n, 2))
+            per.append([list(np.concatenate([xy, xy + wh], 1).astype(np.float32)), list(rng.randint(0, 80, n).astype(np.int64)),
+                        list(rng.uniform(0.05, 1, n).astype(np.float32))])
+        passes.append(per)
+    ms = timed(lambda: merge_tta_predictions(passes, device=device), reps=5, warm=2)
+    out["merge_tta_predictions (64 images x 5 passes: pack + H2D + rn_nms_batch + one D2H)"] = {"ms": round(ms, 3), "launches": 3, "d2h_copies": 1}
+
+    # mAP: 2000 images x 80 classes x 10 thresholds
+    N = 2000
+    predictions, targets = [], []
+    for i in range(N):
+        nt = int(rng.randint(0, 8))
+        xy = rng.uniform(0, 600, size=(nt, 2)); wh = rng.uniform(20, 300, size=(nt, 2))
+        tb = np.concatenate([xy, xy + wh], 1); tcs = rng.randint(0, C, size=nt)
+        targets.append([(tb[j], int(tcs[j])) for j in range(nt)])
+        pb, pc, ps = [], [], []
+        for j in range(nt):
+            for _ in range(int(rng.randint(0, 4))):
+                pb.append((tb[j] + rng.normal(0, 10, size=4)).astype(np.float32)); pc.append(np.int64(tcs[j])); ps.append(np.float32(rng.uniform(0.05, 1)))
+        predictions.append([pb, pc, ps])
+    t0 = time.perf_counter()
+    tab = metrics.mAP_table(predictions, targets, C, metrics.COCO_thresholds, device=device)
+    wall = (time.perf_counter() - t0) * 1e3
+    out["mAP_table (2000 images x 80 classes x 10 thresholds: rn_map_match + rn_map_ap)"] = {
+        "wall_ms_incl_host_packing": round(wall, 1), "table_mean": float(np.nanmean(tab)), "launches": 2, "d2h_copies": 1}
+    return out
 
 
 def cpu_baseline_loss(cfg, max_images=None):
@@ -722,7 +832,9 @@ def run_ours(args):
             "eager": {"api": "SSD_loss()(...) + loss.backward(), call by call", "images_per_s": round(B * args.steps / (eager_ms * 1e-3), 1),
                       "ms_per_step": round(eager_ms / args.steps, 4)},
             "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "h2d_gb_per_s_per_rank": round(h2d * e2e_steps / (e2e_ms * 1e-3) / 1e9, 2),
+                    "limiter": "host->device copy of the step's inputs (pinned memory, PCIe / host fabric): %.1f GB/s per rank; the "
+                               "kernels need %.2f ms of the %.1f ms step" % (h2d * e2e_steps / (e2e_ms * 1e-3) / 1e9, total_ms / args.steps, e2e_ms / e2e_steps)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": measured_traffic("rn_loss_kernel<4,20,true,true,false>", B, 16),
@@ -801,6 +913,13 @@ def run_ours(args):
                                      "backward is removed as well)" % ("sigmoid, " if fl else "")}
             except Exception as exc:
                 line[key] = {"error": repr(exc)}
+        if world == 1 and not args.no_aux:
+            try:
+                import torch
+                torch.cuda.empty_cache()
+                line["aux_kernels"] = time_aux_kernels(device, peak)
+            except Exception as exc:
+                line["aux_kernels"] = {"error": repr(exc)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 tv, tsample = torch_cuda_baseline(COCO, device)
@@ -885,6 +1004,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-b256", action="store_true", help="skip the BASELINE configs[4] extra (256 images over the ranks)")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle check of the first timed batch")
+    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary-kernel measurements (section 8f rows 2-4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

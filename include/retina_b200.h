@@ -57,7 +57,8 @@ int rn_abi_version(void);
 /* Process-wide tuning / test switches (all default 0; nothing is ever read from the environment).  Names:
  *   "assign_dense" (!= 0: rn_assign always takes the dense kernel), "assign_no_balance", "assign_wbase" (dense kernel work
  *   balancing), "loss_iters" (> 0: sub-tiles per CTA of rn_loss), "levels_nchunks" (> 0: class chunks per row tile of
- *   rn_loss_levels), "step_fused" (!= 0: rn_loss_step runs as one persistent kernel where its conditions hold).
+ *   rn_loss_levels), "step_fused" (!= 0: rn_loss_step runs as one persistent kernel where its conditions hold),
+ *   "step_bytemap" (!= 0: rn_loss_step takes its three-kernel byte-map chain instead of rn_assign + rn_loss).
  * rn_set_option returns RN_ERR_INVALID_ARG for an unknown name; rn_get_option returns -1 for one. */
 int rn_set_option(const char *name, int value);
 int rn_get_option(const char *name);
@@ -134,11 +135,12 @@ int rn_loss(const float *clas, const float *reg, const float *gt_boxes, const in
  * (General/Learner.py:514).  Same inputs, outputs and numerics as the two separate calls; pos_thr / neg_thr are the
  * thresholds of match_anchors_objects (0.5 / 0.4).  npos_out [B] (positives per image) and matches_out [B,A] (the
  * rn_assign encoding; costs 4*A*B bytes of stores, meant for inspection and tests) may be NULL.
- * By default the call launches the separate kernels (sparse or dense assignment, streaming loss, final reduction: the
- * fastest variant measured, profiles/r02_summary.md).  After rn_set_option("step_fused", 1), with generated anchors
- * (anchors == NULL), 1 <= M <= 128 and 0.2 <= neg_thr <= pos_thr, the step is a single persistent kernel (rn_step.cu):
- * warps take ground-truth boxes by ticket and write one byte per non-background anchor, the CTAs draw chunks of the B*A
- * rows by ticket, and the last CTA reduces.
+ * By default the call launches the kernels of rn_assign + rn_loss (background fill, one CTA per ground-truth box, the
+ * streaming loss kernel, the final reduction; chained with programmatic dependent launch) -- the fastest variant measured
+ * (profiles/r02_summary.md).  Two alternatives exist behind options, for generated anchors (anchors == NULL), M < 128 and
+ * 0.2 <= neg_thr <= pos_thr: rn_set_option("step_bytemap", 1): three kernels around a persistent all-zero BYTE map kept in
+ * `state` (no fill, no [B,A] int32 array; the final reduction zeroes the written bytes again);
+ * rn_set_option("step_fused", 1): one persistent kernel (rn_step.cu).  All three give identical gradients.
  * Two caller-owned buffers, both 256-byte aligned, one pair per stream: `workspace` (rn_loss_step_workspace_bytes) is
  * plain scratch; `state` (rn_loss_step_state_bytes) must be ZERO-INITIALISED once before its first use
  * (rn_loss_step_state_init, or any memset) and every call leaves it all-zero again, whatever the shapes -- so one

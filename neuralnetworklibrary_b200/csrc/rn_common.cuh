@@ -42,9 +42,14 @@ enum RnOption {
     RN_OPT_LOSS_ITERS,         // > 0: sub-tiles per CTA of the flat loss kernel
     RN_OPT_LVL_NCHUNKS,        // > 0: class chunks per row tile of the level-tensor loss
     RN_OPT_STEP_FUSED,         // != 0: rn_loss_step runs as ONE persistent kernel (rn_step.cu) where its conditions hold
+    RN_OPT_STEP_BYTEMAP,       // != 0: rn_loss_step takes its three-kernel byte-map chain instead of rn_assign + rn_loss
     RN_OPT_COUNT
 };
 int rn_opt(int id);
+
+// Internal entry points shared by the translation units of the library (not part of the C ABI).
+int rn_assign_bytes(const float *gt_boxes, const int64_t *gt_cats, int B, int M, const RnGeom &g, float pos_thr, float neg_thr,
+                    uint8_t *m8, int32_t *npos_acc, int32_t *clean_list, int32_t *clean_cnt, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
 // Loads / stores

@@ -17,6 +17,8 @@
 // partial per CTA, then a one-CTA final kernel (one warp per image) that sums each image's partials in a
 // fixed order in float64 and combines the images in image order.  No floating-point atomics anywhere
 // => run-to-run bit-identical results.
+#include <string.h>
+
 #include "rn_loss_math.cuh"
 
 #ifndef RN_LOSS_CTAS
@@ -29,7 +31,8 @@
 // __launch_bounds__(256, 3): three resident CTAs per SM need <= 85 registers per thread.  Without the
 // bound ptxas drifted from 80 to 88 registers after an unrelated parameter-struct change, dropping
 // occupancy to two CTAs per SM and the kernel from 370 us to 419 us (profiles/r01_summary.md).
-template <int V, int CVT, bool G2, bool GRAD, bool LOGITS>
+// MT: where the assignment comes from (RnMatchI32: rn_assign's int32 matches; RnMatchU8: the byte map of rn_loss_step).
+template <int V, int CVT, bool G2, bool GRAD, bool LOGITS, typename MT>
 __global__ void __launch_bounds__(RN_THREADS, RN_LOSS_CTAS)
 rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ RnGeom g) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -59,16 +62,16 @@ rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ R
     const float gl = __fdiv_rn(P.wc_over_bs, n_norm);  // upstream of every focal term
     const float *x_img = P.clas + (size_t)b * A * P.C;
     float *dx_img = GRAD ? P.dclas + (size_t)b * A * P.C : nullptr;
-    const int32_t *m_img = P.matches + (size_t)b * A;
+    const typename MT::T *m_img = MT::base(P) + (size_t)b * A;
     __syncthreads();  // s_cat / s_box visible
 
     float acc_neg = 0.0f, acc_pos = 0.0f;
 #pragma unroll 1
     for (int tile0 = cta0; tile0 < cta1; tile0 += RN_LOSS_TILE) {
         if (tile0 + RN_LOSS_TILE <= nvec)
-            rn_loss_subtile<V, CVT, G2, GRAD, true, LOGITS, RnMatchI32>(P, b, x_img, dx_img, m_img, s_cat, CV, nvec, nvec, tile0, gl, acc_neg, acc_pos);
+            rn_loss_subtile<V, CVT, G2, GRAD, true, LOGITS, MT>(P, b, x_img, dx_img, m_img, s_cat, CV, nvec, nvec, tile0, gl, acc_neg, acc_pos);
         else
-            rn_loss_subtile<V, CVT, G2, GRAD, false, LOGITS, RnMatchI32>(P, b, x_img, dx_img, m_img, s_cat, CV, nvec, nvec, tile0, gl, acc_neg, acc_pos);
+            rn_loss_subtile<V, CVT, G2, GRAD, false, LOGITS, MT>(P, b, x_img, dx_img, m_img, s_cat, CV, nvec, nvec, tile0, gl, acc_neg, acc_pos);
     }
 
     // ---- regression rows whose first vector lies in this CTA's range: smooth L1 (Vision.py:1532-1566) ----
@@ -81,7 +84,8 @@ rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ R
         const float4 *reg4 = reinterpret_cast<const float4 *>(P.reg) + (size_t)b * A;
         float4 *dreg4 = GRAD ? reinterpret_cast<float4 *>(P.dreg) + (size_t)b * A : nullptr;
         for (int row = r0 + tid; row < r1; row += RN_THREADS) {
-            const int m = __ldg(m_img + row);
+            const int m = MT::load(m_img, row);
+            if (sizeof(typename MT::T) == 1 && P.matches_out) P.matches_out[(size_t)b * A + row] = m;
             float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (m >= 0) {
                 g4 = rn_smooth_l1_row(rn_anchor_from_param(g, P.table, row), s_box[m], __ldg(reg4 + row), ge, acc_reg);
@@ -163,28 +167,38 @@ extern "C" size_t rn_loss_workspace_bytes(int B, int A, int C) {
     return ((partials + 255) / 256) * 256 + ((per_image + 255) / 256) * 256;
 }
 
-template <int V, int CVT, bool LOGITS>
+template <int V, int CVT, bool LOGITS, typename MT>
 static void rn_launch_loss(bool g2, bool grad, dim3 grid, size_t smem, cudaStream_t s, const RnLossParams &P,
                            const RnGeom &g) {
-    if (g2 && grad) rn_launch_pdl(rn_loss_kernel<V, CVT, true, true, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
-    else if (g2) rn_launch_pdl(rn_loss_kernel<V, CVT, true, false, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
-    else if (grad) rn_launch_pdl(rn_loss_kernel<V, CVT, false, true, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
-    else rn_launch_pdl(rn_loss_kernel<V, CVT, false, false, LOGITS>, grid, dim3(RN_THREADS), smem, s, P, g);
+    if (g2 && grad) rn_launch_pdl(rn_loss_kernel<V, CVT, true, true, LOGITS, MT>, grid, dim3(RN_THREADS), smem, s, P, g);
+    else if (g2) rn_launch_pdl(rn_loss_kernel<V, CVT, true, false, LOGITS, MT>, grid, dim3(RN_THREADS), smem, s, P, g);
+    else if (grad) rn_launch_pdl(rn_loss_kernel<V, CVT, false, true, LOGITS, MT>, grid, dim3(RN_THREADS), smem, s, P, g);
+    else rn_launch_pdl(rn_loss_kernel<V, CVT, false, false, LOGITS, MT>, grid, dim3(RN_THREADS), smem, s, P, g);
 }
 
-static int rn_loss_impl(bool logits, float *probs, const float *clas, const float *reg, const float *gt_boxes,
-                        const int64_t *gt_cats, const int32_t *matches, const int32_t *npos, int B, int A, int C, int M,
-                        int H, int W, const double *base, int K, const float *anchors, double alpha, double gamma,
-                        double beta, int B_global, float *dclas, float *dreg, float *out3, void *workspace,
-                        size_t workspace_bytes, void *stream);
+template <typename MT>
+static void rn_dispatch_loss(bool logits, int V, int C, bool g2, bool grad, dim3 grid, size_t smem, cudaStream_t s,
+                             const RnLossParams &P, const RnGeom &g) {
+    if (logits) {
+        if (V == 4 && C == 80) rn_launch_loss<4, 20, true, MT>(g2, grad, grid, smem, s, P, g);
+        else if (V == 4 && C == 20) rn_launch_loss<4, 5, true, MT>(g2, grad, grid, smem, s, P, g);
+        else if (V == 4) rn_launch_loss<4, 0, true, MT>(g2, grad, grid, smem, s, P, g);
+        else rn_launch_loss<1, 0, true, MT>(g2, grad, grid, smem, s, P, g);
+    } else {
+        if (V == 4 && C == 80) rn_launch_loss<4, 20, false, MT>(g2, grad, grid, smem, s, P, g);
+        else if (V == 4 && C == 20) rn_launch_loss<4, 5, false, MT>(g2, grad, grid, smem, s, P, g);
+        else if (V == 4) rn_launch_loss<4, 0, false, MT>(g2, grad, grid, smem, s, P, g);
+        else rn_launch_loss<1, 0, false, MT>(g2, grad, grid, smem, s, P, g);
+    }
+}
 
 extern "C" int rn_loss(const float *clas, const float *reg, const float *gt_boxes, const int64_t *gt_cats,
                        const int32_t *matches, const int32_t *npos, int B, int A, int C, int M, int H, int W,
                        const double *base, int K, const float *anchors, double alpha, double gamma, double beta,
                        int B_global, float *dclas, float *dreg, float *out3, void *workspace,
                        size_t workspace_bytes, void *stream) {
-    return rn_loss_impl(false, nullptr, clas, reg, gt_boxes, gt_cats, matches, npos, B, A, C, M, H, W, base, K, anchors, alpha,
-                        gamma, beta, B_global, dclas, dreg, out3, workspace, workspace_bytes, stream);
+    return rn_loss_impl(false, nullptr, clas, reg, gt_boxes, gt_cats, matches, npos, nullptr, B, A, C, M, H, W, base, K, anchors,
+                        alpha, gamma, beta, B_global, dclas, dreg, out3, workspace, workspace_bytes, stream);
 }
 
 extern "C" int rn_loss_logits(const float *logits, const float *reg, const float *gt_boxes, const int64_t *gt_cats,
@@ -192,17 +206,19 @@ extern "C" int rn_loss_logits(const float *logits, const float *reg, const float
                               const double *base, int K, const float *anchors, double alpha, double gamma,
                               double beta, int B_global, float *dlogits, float *dreg, float *probs_out, float *out3,
                               void *workspace, size_t workspace_bytes, void *stream) {
-    return rn_loss_impl(true, probs_out, logits, reg, gt_boxes, gt_cats, matches, npos, B, A, C, M, H, W, base, K, anchors, alpha,
-                        gamma, beta, B_global, dlogits, dreg, out3, workspace, workspace_bytes, stream);
+    return rn_loss_impl(true, probs_out, logits, reg, gt_boxes, gt_cats, matches, npos, nullptr, B, A, C, M, H, W, base, K, anchors,
+                        alpha, gamma, beta, B_global, dlogits, dreg, out3, workspace, workspace_bytes, stream);
 }
 
-static int rn_loss_impl(bool logits, float *probs, const float *clas, const float *reg, const float *gt_boxes,
-                        const int64_t *gt_cats, const int32_t *matches, const int32_t *npos, int B, int A, int C, int M,
-                        int H, int W, const double *base, int K, const float *anchors, double alpha, double gamma,
-                        double beta, int B_global, float *dclas, float *dreg, float *out3, void *workspace,
-                        size_t workspace_bytes, void *stream) {
+// bytes != NULL: the assignment is the byte map of rn_loss_step (matches is then the optional dense OUTPUT, npos the
+// persistent counters); the final kernel also restores the map and the counters (rn_step.cu).
+int rn_loss_impl(bool logits, float *probs, const float *clas, const float *reg, const float *gt_boxes,
+                 const int64_t *gt_cats, const int32_t *matches, const int32_t *npos, const RnLossBytes *bytes, int B, int A,
+                 int C, int M, int H, int W, const double *base, int K, const float *anchors, double alpha, double gamma,
+                 double beta, int B_global, float *dclas, float *dreg, float *out3, void *workspace,
+                 size_t workspace_bytes, void *stream) {
     if (B <= 0 || A <= 0 || C <= 0 || M < 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: B=%d A=%d C=%d M=%d", B, A, C, M);
-    if (!clas || !reg || !matches || !npos || !out3 || (M > 0 && (!gt_boxes || !gt_cats)))
+    if (!clas || !reg || (!matches && !bytes) || !npos || !out3 || (M > 0 && (!gt_boxes || !gt_cats)))
         return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: null pointer");
     if ((dclas == nullptr) != (dreg == nullptr))
         return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss: dclas and dreg must both be given or both be NULL");
@@ -223,7 +239,9 @@ static int rn_loss_impl(bool logits, float *probs, const float *clas, const floa
     RnLossParams P;
     P.clas = clas; P.reg = reg;
     P.gt_boxes = reinterpret_cast<const float4 *>(gt_boxes); P.gt_cats = gt_cats;
-    P.matches = matches; P.npos = npos; P.table = reinterpret_cast<const float4 *>(anchors);
+    P.matches = bytes ? nullptr : matches; P.m8 = bytes ? bytes->m8 : nullptr;
+    P.matches_out = bytes ? const_cast<int32_t *>(matches) : nullptr;
+    P.npos = npos; P.table = reinterpret_cast<const float4 *>(anchors);
     P.dclas = dclas; P.dreg = dreg; P.probs = probs;
     P.B = B; P.A = A; P.C = C; P.CV = C / V; P.M = M; P.tiles = tiles; P.iters = rn_loss_iters(B, A, C);
     P.a_pos = (float)alpha; P.a_neg = (float)(1.0 - alpha);  // Vision.py:1526
@@ -243,21 +261,18 @@ static int rn_loss_impl(bool logits, float *probs, const float *clas, const floa
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(tiles, B);
     const bool g2 = (gamma == 2.0), grad = dclas != nullptr;
-    if (logits) {
-        if (V == 4 && C == 80) rn_launch_loss<4, 20, true>(g2, grad, grid, smem, s, P, g);
-        else if (V == 4 && C == 20) rn_launch_loss<4, 5, true>(g2, grad, grid, smem, s, P, g);
-        else if (V == 4) rn_launch_loss<4, 0, true>(g2, grad, grid, smem, s, P, g);
-        else rn_launch_loss<1, 0, true>(g2, grad, grid, smem, s, P, g);
-    } else {
-        if (V == 4 && C == 80) rn_launch_loss<4, 20, false>(g2, grad, grid, smem, s, P, g);
-        else if (V == 4 && C == 20) rn_launch_loss<4, 5, false>(g2, grad, grid, smem, s, P, g);
-        else if (V == 4) rn_launch_loss<4, 0, false>(g2, grad, grid, smem, s, P, g);
-        else rn_launch_loss<1, 0, false>(g2, grad, grid, smem, s, P, g);
-    }
+    if (bytes) rn_dispatch_loss<RnMatchU8NC>(logits, V, C, g2, grad, grid, smem, s, P, g);
+    else rn_dispatch_loss<RnMatchI32>(logits, V, C, g2, grad, grid, smem, s, P, g);
     rc = rn_check_launch("rn_loss");
     if (rc) return rc;
+    RnFinalClean clean;
+    memset(&clean, 0, sizeof(clean));
+    if (bytes) {
+        clean.m8 = bytes->m8; clean.clean_list = bytes->clean_list; clean.clean_cnt = bytes->clean_cnt;
+        clean.npos_acc = bytes->npos_acc; clean.npos_out = bytes->npos_out; clean.A = A;
+    }
     rn_launch_pdl(rn_loss_final_kernel, dim3(1), dim3(1024), 0, s, reinterpret_cast<const float2 *>(P.partials), npos, B,
-                  tiles, w_reg, w_clas, bs, per_image, out3);
+                  tiles, w_reg, w_clas, bs, per_image, out3, clean);
     return rn_check_launch("rn_loss_final");
 }
 

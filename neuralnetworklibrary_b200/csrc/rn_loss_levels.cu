@@ -15,6 +15,7 @@
 // gradient.  A warp therefore reads/writes 32*V*4 contiguous bytes per plane.  Algorithmic bytes are unchanged:
 // 8*A*(C+4) per image with gradients.  No tensor cores: there is no contraction on this path.
 #include <stdlib.h>
+#include <string.h>
 
 #include "rn_loss_math.cuh"
 
@@ -536,7 +537,9 @@ extern "C" int rn_loss_levels(const float *const *clas_levels, const float *cons
     else rn_launch_levels<false>(g2, grad, grid, pl.threads, smem, s, P, g);
     rc = rn_check_launch("rn_loss_levels");
     if (rc) return rc;
+    RnFinalClean clean;
+    memset(&clean, 0, sizeof(clean));
     rn_launch_pdl(rn_loss_final_kernel, dim3(1), dim3(1024), 0, s, reinterpret_cast<const float2 *>(P.partials), npos, B,
-                  pl.grid_x, w_reg, w_clas, bs, per_image, out3);
+                  pl.grid_x, w_reg, w_clas, bs, per_image, out3, clean);
     return rn_check_launch("rn_loss_levels_final");
 }

@@ -175,7 +175,9 @@ struct RnLossParams {
     const float *reg;
     const float4 *gt_boxes;
     const int64_t *gt_cats;
-    const int32_t *matches;
+    const int32_t *matches;   // RnMatchI32: [B][A] from rn_assign
+    const uint8_t *m8;        // RnMatchU8: the byte map of rn_loss_step ([B][A]; 0 background, 255 ignored, 1 + box)
+    int32_t *matches_out;     // RnMatchU8 only, may be NULL: the dense int32 assignment, written by the row owners
     const int32_t *npos;
     const float4 *table;
     float *dclas;
@@ -211,6 +213,7 @@ struct RnVec<1> {
 struct RnMatchI32 {  // matches [B,A] int32 written by rn_assign
     typedef int32_t T;
     static __device__ __forceinline__ int load(const int32_t *p, int i) { return __ldg(p + i); }
+    static __device__ __forceinline__ const int32_t *base(const RnLossParams &P);
 };
 struct RnMatchU8 {  // byte codes of the fused step: 0 background, 255 ignored, 1 + index otherwise
     typedef uint8_t T;
@@ -220,7 +223,17 @@ struct RnMatchU8 {  // byte codes of the fused step: 0 background, 255 ignored, 
         asm volatile("ld.global.u8 %0, [%1];" : "=r"(c) : "l"(p + i));
         return c == 0u ? RN_MATCH_NEG : (c == 255u ? RN_MATCH_IGNORE : (int)c - 1);
     }
+    static __device__ __forceinline__ const uint8_t *base(const RnLossParams &P);
 };
+struct RnMatchU8NC : RnMatchU8 {  // the same byte codes written by an EARLIER kernel (the byte-map chain): read-only path
+    // read as a SIGNED byte the code is the canonical value + 1 (0 -> -1 background, 0xff -> -2 ignored, 1 + m -> m for
+    // m <= 126), so the decode is one subtraction
+    static __device__ __forceinline__ int load(const uint8_t *p, int i) {
+        return (int)__ldg(reinterpret_cast<const signed char *>(p) + i) - 1;
+    }
+};
+__device__ __forceinline__ const int32_t *RnMatchI32::base(const RnLossParams &P) { return P.matches; }
+__device__ __forceinline__ const uint8_t *RnMatchU8::base(const RnLossParams &P) { return P.m8; }
 
 // Smooth-L1 of one positive anchor (Vision.py:1532-1566): anchor `an`, its ground-truth box `tg`, predicted offsets `pr`.
 // ge = (1-beta) / (B * 4 * npos): the mean() backward.  Adds the four loss terms to acc_reg, returns d loss / d reg.
@@ -361,10 +374,32 @@ __device__ __forceinline__ void rn_loss_subtile(const RnLossParams &P, int b, co
 // (Vision.py:1640-1641) and combines (Vision.py:1643-1644).  (Folding this into the loss kernel
 // with a last-CTA election -- __threadfence + ticket atomic per CTA -- was measured slower twice, also when
 // only warp 0 stays for the election: COCO step 0.378 -> 0.393 ms, Pascal 78 -> 87 us; profiles/r01_summary.md.)
+// The byte-map assignment of rn_loss_step as rn_loss_impl receives it (rn_loss.cu, rn_step.cu).
+struct RnLossBytes {
+    uint8_t *m8;
+    const int32_t *clean_list;
+    int32_t *clean_cnt;
+    int32_t *npos_acc;
+    int32_t *npos_out;
+};
+int rn_loss_impl(bool logits, float *probs, const float *clas, const float *reg, const float *gt_boxes,
+                 const int64_t *gt_cats, const int32_t *matches, const int32_t *npos, const RnLossBytes *bytes, int B, int A,
+                 int C, int M, int H, int W, const double *base, int K, const float *anchors, double alpha, double gamma,
+                 double beta, int B_global, float *dclas, float *dreg, float *out3, void *workspace,
+                 size_t workspace_bytes, void *stream);
+
+struct RnFinalClean {  // rn_loss_step: leave the persistent byte map / counters as they were found (all of it may be NULL)
+    uint8_t *m8;               // [B][A]
+    const int32_t *clean_list; // [B][A] anchors whose byte was written
+    int32_t *clean_cnt;        // [B]
+    int32_t *npos_acc;         // [B] the counters `npos` points to
+    int32_t *npos_out;         // [B] or NULL: where the caller wants the positive counts
+    int A;
+};
 static __global__ void __launch_bounds__(1024)
 rn_loss_final_kernel(const float2 *__restrict__ partials, const int32_t *__restrict__ npos, int B, int tiles,
                      float w_reg, float w_clas, float bs, float *__restrict__ per_image /*[B][2]*/,
-                     float *__restrict__ out3) {
+                     float *__restrict__ out3, const RnFinalClean clean) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     rn_pdl_wait();  // launched with PDL behind the loss kernel: its partials must be complete and visible
     for (int b = warp; b < B; b += nwarps) {
@@ -381,14 +416,29 @@ rn_loss_final_kernel(const float2 *__restrict__ partials, const int32_t *__restr
             cs += __shfl_xor_sync(RN_FULL_MASK, cs, o);
             rs += __shfl_xor_sync(RN_FULL_MASK, rs, o);
         }
+        const int n = npos[b];
         if (lane == 0) {
-            const int n = npos[b];
             const float n_norm = fmaxf((float)n, 1.0f);
             per_image[2 * b + 0] = n > 0 ? __fdiv_rn((float)rs, (float)(4 * n)) : 0.0f;  // reg loss of image b
             per_image[2 * b + 1] = __fdiv_rn((float)cs, n_norm);                          // clas loss of image b
         }
+        if (clean.m8 && lane == 0 && clean.npos_out) clean.npos_out[b] = n;
     }
     __syncthreads();
+    if (clean.m8) {  // the loss kernel is complete: zero the bytes the assignment wrote (all threads, image by image) ...
+        for (int b = 0; b < B; ++b) {
+            const int nc = clean.clean_cnt[b];
+            const int32_t *lst = clean.clean_list + (size_t)b * clean.A;
+            uint8_t *mb = clean.m8 + (size_t)b * clean.A;
+#pragma unroll 4
+            for (int i = threadIdx.x; i < nc; i += blockDim.x) mb[__ldg(lst + i)] = 0;
+        }
+        __syncthreads();  // ... and then the counters
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            clean.clean_cnt[b] = 0;
+            clean.npos_acc[b] = 0;
+        }
+    }
     if (threadIdx.x == 0) {
         float reg_total = 0.f, clas_total = 0.f;
         for (int b = 0; b < B; ++b) {

@@ -659,7 +659,7 @@ static RnStepPlan rn_step_plan(long long total_rows, int A, int C, int grid) {
 // again when it ends -- whatever the shapes, so one grow-only zero-initialised buffer serves calls of any shape.  `workspace`
 // is plain scratch.
 struct RnStepState {
-    size_t ctrl, done, npos_acc, m8, total;
+    size_t ctrl, done, npos_acc, clean_cnt, m8, total;
 };
 static RnStepState rn_step_state_layout(int B, int A) {
     RnStepState w;
@@ -667,12 +667,13 @@ static RnStepState rn_step_state_layout(int B, int A) {
     w.ctrl = o;      o += rn_up256(sizeof(RnStepCtrl));
     w.done = o;      o += rn_up256(sizeof(int) * (size_t)B);
     w.npos_acc = o;  o += rn_up256(sizeof(int) * (size_t)B);
+    w.clean_cnt = o; o += rn_up256(sizeof(int) * (size_t)B);
     w.m8 = o;        o += rn_up256((size_t)B * (size_t)A);
     w.total = o;
     return w;
 }
 struct RnStepWs {
-    size_t partials, per_image, matches32, npos32, loss_ws, total;
+    size_t partials, per_image, matches32, npos32, loss_ws, total;  // matches32 doubles as the clean list of the byte-map chain
 };
 static size_t rn_step_max_partials(int B, int A, int C) {
     // the smallest chunk (2 sub-tiles) gives the most chunks; slots is largest for the largest chunk (6 sub-tiles)
@@ -786,6 +787,31 @@ extern "C" int rn_loss_step(const float *clas, const float *reg, const float *gt
 
     const bool fused = !anchors && M >= 1 && M <= RN_STEP_MAXM && neg_thr >= 0.2f && pos_thr >= neg_thr &&
                        (long long)B * A <= 0x7fffffffLL - 65536 && rn_opt(RN_OPT_STEP_FUSED) != 0;
+    const bool bytemap = !fused && !anchors && M >= 1 && M < RN_STEP_MAXM && neg_thr >= 0.2f && pos_thr >= neg_thr &&
+                         rn_opt(RN_OPT_STEP_BYTEMAP) != 0;
+    if (bytemap) {
+        // Opt-in: THREE kernels and no [B,A] int32 array.  One CTA per ground-truth box writes a byte per non-background
+        // anchor into the persistent zeroed map (+ its index into a clean list), the streaming loss kernel reads the bytes,
+        // and the final reduction zeroes them again.  Against the four-kernel chain of rn_assign + rn_loss this removes the
+        // background fill (4 us, 4*A*B bytes written and read back) -- but the fill already overlaps the assignment's
+        // prologue through PDL, the byte loads make the streaming kernel 2 % slower and the cleaning lengthens the
+        // single-CTA final kernel: measured COCO B=16 0.359 vs 0.353 ms, Pascal B=32 75 vs 65 us (profiles/r02_summary.md).
+        RnGeom g;
+        int rc = rn_build_geom(&g, H, W, base, K, nullptr, A);
+        if (rc) return rc;
+        RnLossBytes by;
+        by.m8 = zs + Z.m8;
+        by.clean_list = reinterpret_cast<const int32_t *>(ws + L.matches32);
+        by.clean_cnt = reinterpret_cast<int32_t *>(zs + Z.clean_cnt);
+        by.npos_acc = reinterpret_cast<int32_t *>(zs + Z.npos_acc);
+        by.npos_out = npos_out;
+        rc = rn_assign_bytes(gt_boxes, gt_cats, B, M, g, pos_thr, neg_thr, by.m8, by.npos_acc,
+                             reinterpret_cast<int32_t *>(ws + L.matches32), by.clean_cnt, s);
+        if (rc) return rc;
+        return rn_loss_impl(from_logits != 0, from_logits ? probs_out : nullptr, clas, reg, gt_boxes, gt_cats, matches_out,
+                            by.npos_acc, &by, B, A, C, M, H, W, base, K, nullptr, alpha, gamma, beta, B_global, dclas, dreg, out3,
+                            ws + L.loss_ws, rn_loss_workspace_bytes(B, A, C), stream);
+    }
     if (!fused) {  // the separate kernels: rn_assign (dense or sparse) + rn_loss
         int32_t *m32 = matches_out ? matches_out : reinterpret_cast<int32_t *>(ws + L.matches32);
         int32_t *n32 = npos_out ? npos_out : reinterpret_cast<int32_t *>(ws + L.npos32);

@@ -51,7 +51,7 @@ def assign_batch(anchors, gt_boxes, gt_cats, pos_thresh=0.5, neg_thresh=0.4, wan
 
 def _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, need_grad, bufs=None):
     """rn_loss_step on the current stream: assignment + loss forward/backward + final reduction in one library call (the
-    separate kernels by default, ONE persistent kernel after rn_set_option("step_fused", 1)).
+    kernels of rn_assign + rn_loss by default; a byte-map chain or ONE persistent kernel behind rn_set_option).
     Returns (out3, dreg, dclas, matches, npos); `matches` is None unless cfg["keep_matches"]; `bufs` lets a caller
     (CUDA-graph capture) supply persistent output tensors and the zero-initialised workspace."""
     lib = _lib.load()
@@ -271,12 +271,15 @@ class CapturedLossStep(object):
         self.loss, self.reg_loss, self.clas_loss = self.out3.unbind(0)
         self.dreg, self.dclas = self.bufs["dreg"], self.bufs["dclas"]
         self.npos = self.bufs["npos"]
-        # fused: rn_step_kernel only.  Otherwise rn_assign (fill + sparse, or a memset node + dense), loss, final reduction.
+        # default: rn_assign (fill + sparse = 2 kernels, or a memset node + the dense kernel) + loss + final reduction.
+        # Options: byte-map chain (3 kernels), fused step (rn_step_kernel only).
+        sparse = anchor_args(anchors)[4] is None and 1 <= int(gt_cats.shape[1]) <= 128 and cfg["neg_thresh"] >= 0.2 \
+            and cfg["pos_thresh"] >= cfg["neg_thresh"]
         if _step_is_fused(anchors, gt_cats, cfg):
             self.kernels_per_replay = 1
+        elif sparse and int(gt_cats.shape[1]) < 128 and _lib.load().rn_get_option(b"step_bytemap") > 0:
+            self.kernels_per_replay = 3
         else:
-            sparse = anchor_args(anchors)[4] is None and 1 <= int(gt_cats.shape[1]) <= 128 and cfg["neg_thresh"] >= 0.2 \
-                and cfg["pos_thresh"] >= cfg["neg_thresh"]
             self.kernels_per_replay = 4 if sparse else 3
 
     @property
