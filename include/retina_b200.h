@@ -185,6 +185,17 @@ int rn_loss_levels(const float *const *clas_levels /*host[5]*/, const float *con
                    float *const *dreg_levels /*host[5] or NULL*/, float *const *probs_levels /*host[5] or NULL*/,
                    float *out3, void *workspace, size_t workspace_bytes, void *stream);
 
+/* The one exchange of the image-sharded multi-GPU path: out3 (this rank's additive share of
+ * {loss, reg_loss, clas_loss}) is replaced by the sum over all ranks, computed in rank order (bit-identical on every rank)
+ * by ONE tiny kernel on `stream` -- capturable in the step's CUDA graph -- that stores the three scalars into every peer's
+ * buffer through peer-mapped memory (NVLink), publishes them with a release store of a sequence number and waits for the
+ * peers' with acquire loads.  peer_bufs: HOST array of `world` device pointers, peer_bufs[r] = rank r's buffer of
+ * rn_peer_exchange_bytes(world) bytes as mapped into THIS process (e.g. torch symmetric memory / CUDA IPC), zeroed once
+ * before the first use; seq: one zero-initialised uint32 in local device memory.  world <= 16.  Every rank must call it
+ * the same number of times (the kernel waits for its peers). */
+size_t rn_peer_exchange_bytes(int world);
+int rn_peer_exchange(float *out3, void *const *peer_bufs /*host [world]*/, int rank, int world, uint32_t *seq, void *stream);
+
 /* Backward with a non-unit upstream gradient: scales dclas[n_clas], dreg[n_reg] in place by the
  * DEVICE scalar *grad_out; the kernel exits immediately when *grad_out == 1 (what loss.backward()
  * passes, General/Learner.py:514), so the common case costs one empty launch and no host sync. */

@@ -25,8 +25,10 @@ def _targets(target, device):
     BBoxes, Cats = target[0], target[1]
     _lib.require_cuda(BBoxes, "BBoxes")
     _lib.require_cuda(Cats, "Cats")
-    gt_boxes = BBoxes.detach().to(dtype=torch.float32).contiguous()
-    gt_cats = Cats.detach().to(dtype=torch.int64).contiguous()
+    # (the common case -- float32 / int64, contiguous, no grad -- costs no torch call at all: this runs once per step)
+    gt_boxes = BBoxes if (BBoxes.dtype == torch.float32 and BBoxes.is_contiguous() and not BBoxes.requires_grad) \
+        else BBoxes.detach().to(dtype=torch.float32).contiguous()
+    gt_cats = Cats if (Cats.dtype == torch.int64 and Cats.is_contiguous()) else Cats.detach().to(dtype=torch.int64).contiguous()
     if gt_boxes.dim() != 3 or gt_boxes.shape[2] != 4 or gt_cats.shape != gt_boxes.shape[:2]:
         raise ValueError("target must be [BBoxes (bs x M x 4), Cats (bs x M)]")
     return gt_boxes, gt_cats
@@ -119,7 +121,7 @@ class _SSDLossFunction(torch.autograd.Function):
         else:
             out3, dreg, dclas, matches, npos = _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, need_grad)
         if cfg["world_size"] > 1:
-            out3 = reduce_loss_scalars(out3, cfg["group"])
+            out3 = cfg["exchange"](out3) if cfg.get("exchange") is not None else reduce_loss_scalars(out3, cfg["group"])
         ctx.grads = (dreg, dclas)
         ctx.used = False
         cfg["last_matches"], cfg["last_npos"] = matches, npos
@@ -139,8 +141,12 @@ class _SSDLossFunction(torch.autograd.Function):
         ctx.used = True
         ctx.grads = None  # hand over the only reference: autograd then adopts the buffers instead of cloning 1 GB
         lib = _lib.load()
-        g = g_loss.detach().to(dtype=torch.float32).contiguous()
-        with torch.cuda.device(dclas.device):
+        g = g_loss if (g_loss.dtype == torch.float32 and g_loss.is_contiguous()) else g_loss.detach().to(dtype=torch.float32).contiguous()
+        if dclas.device.index != torch.cuda.current_device():
+            with torch.cuda.device(dclas.device):
+                _lib.check(lib.rn_scale_grads(_lib.ptr(dclas), dclas.numel(), _lib.ptr(dreg), dreg.numel(), _lib.ptr(g),
+                                              _lib.stream_ptr(dclas.device)))
+        else:
             _lib.check(lib.rn_scale_grads(_lib.ptr(dclas), dclas.numel(), _lib.ptr(dreg), dreg.numel(), _lib.ptr(g),
                                           _lib.stream_ptr(dclas.device)))
         return dreg, dclas, None, None, None, None
@@ -260,13 +266,19 @@ class CapturedLossStep(object):
             self.bufs["matches"] = torch.empty((B, A), dtype=torch.int32, device=dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):   # warm-up outside capture (lazy module load)
+        exchange = cfg.get("exchange")
+        with torch.cuda.stream(side):   # warm-up outside capture (lazy module load); every rank runs the same sequence
             _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, True, self.bufs)
+            if exchange is not None:
+                exchange(self.bufs["out3"])
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, True, self.bufs)
+            if exchange is not None:
+                exchange(self.bufs["out3"])
+        self.exchange_in_graph = exchange is not None
         self.out3 = self.bufs["out3"]
         self.loss, self.reg_loss, self.clas_loss = self.out3.unbind(0)
         self.dreg, self.dclas = self.bufs["dreg"], self.bufs["dclas"]
@@ -281,6 +293,7 @@ class CapturedLossStep(object):
             self.kernels_per_replay = 3
         else:
             self.kernels_per_replay = 4 if sparse else 3
+        self.kernels_per_replay += 1 if self.exchange_in_graph else 0
 
     @property
     def matches(self):
@@ -339,6 +352,39 @@ def reduce_loss_scalars(out3, group=None):
     return gathered.sum(dim=0)
 
 
+class PeerExchange(object):
+    """The loss exchange of the image-sharded path without NCCL on the step's critical path: rn_peer_exchange, one tiny
+    kernel on the step's own stream (capturable in its CUDA graph) that stores this rank's three scalars into every peer's
+    buffer through peer-mapped memory over NVLink and sums all ranks' scalars in rank order (bit-identical on every rank).
+    The buffers are torch symmetric memory (torch.distributed._symmetric_memory: allocation + rendezvous are plumbing, the
+    kernel is this library's).  Construction is a collective; afterwards every rank must call the exchange the same number
+    of times."""
+
+    def __init__(self, group=None, device=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        lib = _lib.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        nbytes = int(lib.rn_peer_exchange_bytes(self.world))
+        self.buf = symm_mem.empty((nbytes + 3) // 4, dtype=torch.float32, device=dev)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)   # every rank's buffer is zeroed before any rank stores into it
+        self.ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
+        self.seq = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def __call__(self, out3):
+        """Replaces out3 (this rank's share) by the sum over the ranks, in place, on the current stream."""
+        _lib.check(_lib.load().rn_peer_exchange(_lib.ptr(out3), self.ptrs, self.rank, self.world, _lib.ptr(self.seq),
+                                                _lib.stream_ptr(out3.device)))
+        return out3
+
+
 class SSD_loss(object):
     """SSD / RetinaNet loss: (1-beta) * smooth-L1 + beta * focal (reference Vision.py:1607-1644).
 
@@ -348,8 +394,12 @@ class SSD_loss(object):
     12-byte NCCL exchange; per-rank reg/clas gradients need no communication."""
 
     def __init__(self, beta=0.5, alpha=0.25, gamma=2.0, distributed=False, process_group=None, global_batch=None,
-                 from_logits=False, keep_probs=False, keep_matches=False):
+                 from_logits=False, keep_probs=False, keep_matches=False, peer_exchange=False):
         self.beta, self.alpha, self.gamma = beta, alpha, gamma
+        # peer_exchange (with distributed=True): sum the loss scalars with rn_peer_exchange (a kernel over peer-mapped
+        # memory on the step's own stream, part of the captured graph) instead of a NCCL all-gather; True creates the
+        # PeerExchange on first use (a collective), or pass one.
+        self.peer_exchange = peer_exchange
         self.keep_probs = bool(keep_probs)   # from_logits only: also store sigmoid(logits) in .last_probs
         # keep_matches: the step also writes its dense [bs,A] int32 assignment (4*A*bs bytes of extra stores; for
         # inspection and tests).  Without it last_assignment computes the matches on demand with rn_assign.
@@ -379,12 +429,21 @@ class SSD_loss(object):
         cfg = dict(alpha=self.alpha, gamma=self.gamma, beta=self.beta, pos_thresh=self.pos_thresh,
                    neg_thresh=self.neg_thresh, world_size=world, group=self.process_group,
                    global_batch=self.global_batch, from_logits=self.from_logits, want_probs=self.keep_probs,
-                   keep_matches=self.keep_matches)
-        loss, reg_loss, clas_loss = _SSDLossFunction.apply(reg.contiguous(), clas.contiguous(), anchors, gt_boxes,
-                                                           gt_cats, cfg)
+                   keep_matches=self.keep_matches, exchange=self._exchange() if world > 1 else None)
+        loss, reg_loss, clas_loss = _SSDLossFunction.apply(reg if reg.is_contiguous() else reg.contiguous(),
+                                                           clas if clas.is_contiguous() else clas.contiguous(), anchors,
+                                                           gt_boxes, gt_cats, cfg)
         self._cfg = cfg
         self.reg_loss, self.clas_loss = reg_loss, clas_loss   # Vision.py:1643
         return loss
+
+    def _exchange(self):
+        """The PeerExchange of this loss (created on first use), or None for the NCCL all-gather."""
+        if not self.peer_exchange or not self.distributed:
+            return None
+        if self.peer_exchange is True:
+            self.peer_exchange = PeerExchange(self.process_group)
+        return self.peer_exchange
 
     def _cfg_for_call(self):
         world = 1
@@ -408,8 +467,10 @@ class SSD_loss(object):
         return loss
 
     def capture(self, activ, target):
-        """Captures forward+backward for the given static tensors into a CUDA graph (single-GPU loss
-        only; the multi-GPU scalar exchange stays outside the graph).  Returns a CapturedLossStep."""
+        """Captures forward+backward for the given static tensors into a CUDA graph.  Returns a CapturedLossStep.  With
+        distributed=True and peer_exchange the sum of the loss scalars over the ranks (rn_peer_exchange) is part of the graph
+        and .loss / .reg_loss / .clas_loss hold the global values; with the NCCL exchange the graph holds this rank's share
+        and the caller reduces it (reduce_loss_scalars)."""
         anchors, reg, clas = activ[0], activ[1], activ[2]
         BBoxes, Cats = target[0], target[1]
         _lib.require_cuda(BBoxes, "BBoxes", torch.float32)
@@ -427,7 +488,7 @@ class SSD_loss(object):
                 raise ValueError("capture() needs contiguous static tensors")
         cfg = dict(alpha=self.alpha, gamma=self.gamma, beta=self.beta, pos_thresh=self.pos_thresh,
                    neg_thresh=self.neg_thresh, world_size=1, group=None, global_batch=self.global_batch,
-                   from_logits=self.from_logits, keep_matches=self.keep_matches)
+                   from_logits=self.from_logits, keep_matches=self.keep_matches, exchange=self._exchange())
         return CapturedLossStep(cfg, anchors, reg.detach(), clas.detach(), BBoxes, Cats)
 
     @property

@@ -55,6 +55,29 @@ def main():
     dist.all_gather(every, ls.detach().reshape(1))
     assert all(torch.equal(every[0], e) for e in every), "loss differs between ranks"
 
+    # the same shard through the peer-memory exchange (rn_peer_exchange): bit-identical to the NCCL all-gather + rank-order sum,
+    # eagerly and as CUDA-graph replays with the exchange inside the graph
+    peer_ok = "skipped"
+    try:
+        from neuralnetworklibrary_b200.vision import PeerExchange
+        px = PeerExchange()
+    except Exception as exc:   # no symmetric memory on this box: the NCCL path stands
+        px, peer_ok = None, "unavailable (%s)" % type(exc).__name__
+    if px is not None:
+        peer = SSD_loss(distributed=True, global_batch=B, peer_exchange=px)
+        rs2, cs2 = activ[1].clone().requires_grad_(True), activ[2].clone().requires_grad_(True)
+        lp = peer([anchors, rs2, cs2], target)
+        lp.backward()
+        assert lp.item() == ls.item() and peer.reg_loss.item() == shard.reg_loss.item() and peer.clas_loss.item() == shard.clas_loss.item()
+        assert torch.equal(cs2.grad, cs.grad) and torch.equal(rs2.grad, rs.grad)
+        cap = peer.capture([anchors, activ[1].contiguous(), activ[2].contiguous()], [target[0].contiguous(), target[1].contiguous()])
+        for _ in range(5):
+            cap.replay()
+        torch.cuda.synchronize()
+        assert cap.exchange_in_graph and cap.loss.item() == ls.item(), (cap.loss.item(), ls.item())
+        assert torch.equal(cap.dclas, cs.grad)
+        peer_ok = "ok (%d kernels per replay)" % cap.kernels_per_replay
+
     # detections: shard + gather == full batch
     ci, ri = syn.make_infer_activations(B, an.shape[0], C, seed=78, anchors=an, mu=-5.0, clusters=5)
     bp = BBoxPredictor()
@@ -68,8 +91,8 @@ def main():
             assert len(x) == len(y) and all(np.array_equal(u, v) for u, v in zip(x, y))
     dist.barrier()
     if rank == 0:
-        print("dist_gpu_check ok: world=%d loss=%.6f (single GPU %.6f), shards %s" %
-              (world, ls.item(), lf.item(), [nd.shard_bounds(B, world, r) for r in range(world)]))
+        print("dist_gpu_check ok: world=%d loss=%.6f (single GPU %.6f), shards %s, peer-memory exchange %s" %
+              (world, ls.item(), lf.item(), [nd.shard_bounds(B, world, r) for r in range(world)], peer_ok))
     dist.destroy_process_group()
 
 
