@@ -170,10 +170,17 @@ extern "C" size_t rn_loss_workspace_bytes(int B, int A, int C) {
 template <int V, int CVT, bool LOGITS, typename MT>
 static void rn_launch_loss(bool g2, bool grad, dim3 grid, size_t smem, cudaStream_t s, const RnLossParams &P,
                            const RnGeom &g) {
-    if (g2 && grad) rn_launch_pdl(rn_loss_kernel<V, CVT, true, true, LOGITS, MT>, grid, dim3(RN_THREADS), smem, s, P, g);
-    else if (g2) rn_launch_pdl(rn_loss_kernel<V, CVT, true, false, LOGITS, MT>, grid, dim3(RN_THREADS), smem, s, P, g);
-    else if (grad) rn_launch_pdl(rn_loss_kernel<V, CVT, false, true, LOGITS, MT>, grid, dim3(RN_THREADS), smem, s, P, g);
-    else rn_launch_pdl(rn_loss_kernel<V, CVT, false, false, LOGITS, MT>, grid, dim3(RN_THREADS), smem, s, P, g);
+    // the training configuration (gamma == 2 with gradients) has row-width specialisations; the rarer variants (forward only,
+    // general gamma) share the generic row width -- fewer instantiations, a smaller library
+    if (g2 && grad) {
+        rn_launch_pdl(rn_loss_kernel<V, CVT, true, true, LOGITS, MT>, grid, dim3(RN_THREADS), smem, s, P, g);
+    } else if constexpr (CVT != 0) {
+        rn_launch_loss<V, 0, LOGITS, MT>(g2, grad, grid, smem, s, P, g);
+    } else {
+        if (g2) rn_launch_pdl(rn_loss_kernel<V, 0, true, false, LOGITS, MT>, grid, dim3(RN_THREADS), smem, s, P, g);
+        else if (grad) rn_launch_pdl(rn_loss_kernel<V, 0, false, true, LOGITS, MT>, grid, dim3(RN_THREADS), smem, s, P, g);
+        else rn_launch_pdl(rn_loss_kernel<V, 0, false, false, LOGITS, MT>, grid, dim3(RN_THREADS), smem, s, P, g);
+    }
 }
 
 template <typename MT>

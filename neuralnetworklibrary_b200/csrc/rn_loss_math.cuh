@@ -401,8 +401,11 @@ rn_loss_final_kernel(const float2 *__restrict__ partials, const int32_t *__restr
                      float w_reg, float w_clas, float bs, float *__restrict__ per_image /*[B][2]*/,
                      float *__restrict__ out3, const RnFinalClean clean) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    __shared__ float2 s_pi[1024];  // per-image {reg loss, clas loss} (global `per_image` only for larger batches)
+    float2 *pi = B <= 1024 ? s_pi : reinterpret_cast<float2 *>(per_image);
     rn_pdl_wait();  // launched with PDL behind the loss kernel: its partials must be complete and visible
     for (int b = warp; b < B; b += nwarps) {
+        const int n = npos[b];  // issued ahead of the partial loads, consumed after them
         double cs = 0.0, rs = 0.0;
         const float2 *p = partials + (size_t)b * tiles;
 #pragma unroll 4
@@ -416,11 +419,10 @@ rn_loss_final_kernel(const float2 *__restrict__ partials, const int32_t *__restr
             cs += __shfl_xor_sync(RN_FULL_MASK, cs, o);
             rs += __shfl_xor_sync(RN_FULL_MASK, rs, o);
         }
-        const int n = npos[b];
         if (lane == 0) {
             const float n_norm = fmaxf((float)n, 1.0f);
-            per_image[2 * b + 0] = n > 0 ? __fdiv_rn((float)rs, (float)(4 * n)) : 0.0f;  // reg loss of image b
-            per_image[2 * b + 1] = __fdiv_rn((float)cs, n_norm);                          // clas loss of image b
+            pi[b] = make_float2(n > 0 ? __fdiv_rn((float)rs, (float)(4 * n)) : 0.0f,  // reg loss of image b
+                                __fdiv_rn((float)cs, n_norm));                         // clas loss of image b
         }
         if (clean.m8 && lane == 0 && clean.npos_out) clean.npos_out[b] = n;
     }
@@ -442,8 +444,8 @@ rn_loss_final_kernel(const float2 *__restrict__ partials, const int32_t *__restr
     if (threadIdx.x == 0) {
         float reg_total = 0.f, clas_total = 0.f;
         for (int b = 0; b < B; ++b) {
-            reg_total = __fadd_rn(reg_total, per_image[2 * b + 0]);
-            clas_total = __fadd_rn(clas_total, per_image[2 * b + 1]);
+            reg_total = __fadd_rn(reg_total, pi[b].x);
+            clas_total = __fadd_rn(clas_total, pi[b].y);
         }
         const float reg_loss = __fdiv_rn(reg_total, bs), clas_loss = __fdiv_rn(clas_total, bs);
         out3[0] = __fadd_rn(__fmul_rn(w_reg, reg_loss), __fmul_rn(w_clas, clas_loss));

@@ -453,9 +453,18 @@ rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t
             const int shift = 64 - done - db;
             for (int i = tid; i < RN_BINS; i += RN_SEL_THREADS) s_hist[i] = 0;
             __syncthreads();
-            for (int i = tid; i < n; i += RN_SEL_THREADS) {
-                const unsigned long long k = kb[i];
-                if (done == 0 || (k >> (64 - done)) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & ((1u << db) - 1u))], 1);
+            // four independent key loads per thread in flight (the pass is a chain of L2 round trips otherwise: 17 k keys per
+            // image over 1024 threads = 17 dependent-latency iterations per pass, ~30 us for the kernel)
+            for (int i0 = tid; i0 < n; i0 += 4 * RN_SEL_THREADS) {
+                unsigned long long k4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) k4[u] = (i0 + u * RN_SEL_THREADS < n) ? __ldg(kb + i0 + u * RN_SEL_THREADS) : 0ull;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned long long k = k4[u];
+                    if (i0 + u * RN_SEL_THREADS < n && (done == 0 || (k >> (64 - done)) == prefix))
+                        atomicAdd(&s_hist[(int)((k >> shift) & ((1u << db) - 1u))], 1);
+                }
             }
             __syncthreads();
             // bins in descending digit order: thread t owns ranks 2t and 2t+1
@@ -478,12 +487,18 @@ rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t
         }
         if (tid == 0) s_n = 0;
         __syncthreads();
-        for (int i = tid; i < n; i += RN_SEL_THREADS) {
-            const unsigned long long k = kb[i];
-            const unsigned long long top = (done == 64) ? k : (k >> (64 - done));
-            if (top >= prefix) {
-                const int pos = atomicAdd(&s_n, 1);
-                if (pos < RN_SORT_N) s_keys[pos] = k;
+        for (int i0 = tid; i0 < n; i0 += 4 * RN_SEL_THREADS) {
+            unsigned long long k4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) k4[u] = (i0 + u * RN_SEL_THREADS < n) ? __ldg(kb + i0 + u * RN_SEL_THREADS) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long k = k4[u];
+                const unsigned long long top = (done == 64) ? k : (k >> (64 - done));
+                if (i0 + u * RN_SEL_THREADS < n && top >= prefix) {
+                    const int pos = atomicAdd(&s_n, 1);
+                    if (pos < RN_SORT_N) s_keys[pos] = k;
+                }
             }
         }
         __syncthreads();
