@@ -163,11 +163,14 @@ def time_loss_graph(anchors, sets, steps, warmup, device, world, from_logits=Fal
     if world > 1:
         try:
             loss_fn = SSD_loss(global_batch=sets[0][0].shape[0] * world, from_logits=from_logits, distributed=True,
-                               peer_exchange=PEER["obj"] if PEER.get("obj") is not None else True)
+                               peer_exchange=PEER["obj"] if PEER.get("obj") is not None else (False if PEER.get("failed") else True))
             PEER["obj"] = loss_fn._exchange()
+            if PEER["obj"] is None:
+                raise RuntimeError("symmetric memory unavailable on some rank")
             EXCHANGE["kind"] = "rn_peer_exchange: one kernel over peer-mapped (symmetric) memory inside the step's CUDA graph"
         except Exception as exc:
             loss_fn = None
+            PEER["failed"] = True
             EXCHANGE["kind"] = "nccl all_gather_into_tensor on a side stream (peer-memory exchange unavailable: %s)" % type(exc).__name__
     in_graph = loss_fn is not None
     if loss_fn is None:

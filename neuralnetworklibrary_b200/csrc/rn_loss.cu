@@ -306,6 +306,7 @@ rn_peer_exchange_kernel(float *__restrict__ out3, const RnPeers peers, int rank,
     const uint32_t e = *seq + 1u;
     const int set = (int)(e & 1u);
     const float v0 = out3[0], v1 = out3[1], v2 = out3[2];
+    bool timed_out = false;
     if (t < world) {
         float *slot = peers.buf[t] + ((size_t)set * world + rank) * 4;
         slot[0] = v0;
@@ -314,14 +315,30 @@ rn_peer_exchange_kernel(float *__restrict__ out3, const RnPeers peers, int rank,
         __threadfence_system();
         uint32_t *flag = reinterpret_cast<uint32_t *>(peers.buf[t] + (size_t)2 * world * 4) + (size_t)set * world + rank;
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(e) : "memory");
-        // wait until rank t has published this step into MY buffer
+        // wait until rank t has published this step into MY buffer -- but never forever: a peer that died (or never launched
+        // its step) must not hang the GPU; after ~5 s the exchange gives up and poisons the result
         const uint32_t *mine = reinterpret_cast<const uint32_t *>(peers.buf[rank] + (size_t)2 * world * 4) + (size_t)set * world + t;
         uint32_t got;
+        unsigned long long t0, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(mine) : "memory");
-        } while ((int)(got - e) < 0);
+            if ((int)(got - e) >= 0) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 5000000000ull) {
+                timed_out = true;
+                break;
+            }
+            __nanosleep(100);
+        } while (true);
     }
-    __syncwarp();
+    timed_out = __any_sync(RN_FULL_MASK, timed_out);
+    if (t == 0 && timed_out) {
+        out3[0] = out3[1] = out3[2] = __int_as_float(0x7fc00000);  // NaN: loud, and the next step is not blocked by this one
+        *seq = e;
+        return;
+    }
+    if (timed_out) return;
     if (t == 0) {
         const float *slots = peers.buf[rank] + (size_t)set * world * 4;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;

@@ -378,6 +378,20 @@ class PeerExchange(object):
         self.ptrs = (C.c_void_p * self.world)(*[int(p) for p in self.handle.buffer_ptrs])
         self.seq = torch.zeros(1, dtype=torch.int32, device=dev)
 
+    @classmethod
+    def create(cls, group=None, device=None):
+        """A PeerExchange if EVERY rank of the group could set one up, else None on every rank (a collective: the ranks
+        agree through one NCCL all-reduce, so that no rank waits in rn_peer_exchange for a peer that fell back to NCCL)."""
+        import torch.distributed as dist
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        try:
+            px, ok = cls(group, dev), 1
+        except Exception:
+            px, ok = None, 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return px if int(flag.item()) == 1 else None
+
     def __call__(self, out3):
         """Replaces out3 (this rank's share) by the sum over the ranks, in place, on the current stream."""
         _lib.check(_lib.load().rn_peer_exchange(_lib.ptr(out3), self.ptrs, self.rank, self.world, _lib.ptr(self.seq),
@@ -442,8 +456,8 @@ class SSD_loss(object):
         if not self.peer_exchange or not self.distributed:
             return None
         if self.peer_exchange is True:
-            self.peer_exchange = PeerExchange(self.process_group)
-        return self.peer_exchange
+            self.peer_exchange = PeerExchange.create(self.process_group) or False   # False: every rank falls back to NCCL
+        return self.peer_exchange or None
 
     def _cfg_for_call(self):
         world = 1

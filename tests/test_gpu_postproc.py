@@ -162,3 +162,31 @@ def test_postproc_full_size(H, W, C, B, seed):
         # idempotence: NMS of the survivors keeps all of them
         keep = orc.nms(b, c, s, max_boxes=1000)
         assert len(keep) == n
+
+
+def test_nms_batch_ragged_images_match_single_calls():
+    """rn_nms_batch (one launch sequence for L images, survivors gathered on the device) against nms() image by image and the
+    oracle: empty images, a one-box image, an image with more candidates than top_k, top_k < max_boxes."""
+    from neuralnetworklibrary_b200.retinanet import decode_nms_buffer, nms, nms_batch_device
+    rng = np.random.RandomState(21)
+    sizes = [0, 1, 37, 0, 900, 5, 2600]
+    boxes, classes, scores = [], [], []
+    for n in sizes:
+        xy = rng.uniform(0, 500, (n, 2)); wh = rng.uniform(8, 150, (n, 2))
+        boxes.append(np.concatenate([xy, xy + wh], 1).astype(np.float32))
+        classes.append(rng.randint(0, 5, n).astype(np.int64))
+        scores.append(rng.permutation(np.linspace(0.05, 0.99, max(n, 1))[:n]).astype(np.float32))   # tie-free
+    offs = np.zeros(len(sizes) + 1, np.int32)
+    offs[1:] = np.cumsum(sizes)
+    d = lambda a, dt: torch.from_numpy(np.concatenate(a).astype(dt)).to(dev())
+    for top_k, max_keep in ((1000, 20), (50, 50), (2048, 300)):
+        buf, K = nms_batch_device(d(boxes, np.float32).view(-1, 4), d(classes, np.int64), d(scores, np.float32),
+                                  torch.from_numpy(offs).to(dev()), 0.5, top_k, max_keep)
+        kb, kc, ks, ki, cnt = decode_nms_buffer(buf.cpu().numpy(), len(sizes), K)
+        for l, n in enumerate(sizes):
+            keep = orc.nms(boxes[l], classes[l], scores[l], top_k=top_k, max_boxes=max_keep) if n else np.zeros(0, np.int32)
+            assert int(cnt[l]) == len(keep)
+            assert np.array_equal(ki[l, :len(keep)], keep)
+            assert np.array_equal(kb[l, :len(keep)], boxes[l][keep]) and np.array_equal(ks[l, :len(keep)], scores[l][keep])
+            rb, rc, rs = nms(boxes[l], classes[l], scores[l], top_k=top_k, max_boxes=max_keep) if n else ([], [], [])
+            assert len(rb) == len(keep) and (not len(keep) or np.array_equal(np.array(rc), classes[l][keep]))

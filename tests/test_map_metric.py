@@ -119,3 +119,30 @@ def test_map_empty_inputs():
     t = metrics.mAP_table([[[np.array([0, 0, 10, 10], np.float32)], [np.int64(0)], [np.float32(0.9)]]], [[]], 2, [0.5])
     assert np.isnan(t).all()
     assert np.isnan(metrics.mAP([], [], cats, [0.5], verbose=False))
+
+
+@pytest.mark.gpu
+def test_map_many_predictions_per_category_and_score_ties():
+    """Two categories with ~6 000 predictions each: the rank-by-counting sort runs over several shared-memory tiles, the sum over
+    the correct positions goes through NumPy's pairwise recursion (n > 128), and quantised scores produce long runs of equal
+    scores whose order is decided by is_correct (sorted(zip(Scores, IsCorrect), reverse=True), Vision.py:1730)."""
+    from neuralnetworklibrary_b200 import metrics
+    rng = np.random.RandomState(9)
+    N, C = 1500, 2
+    predictions, targets = [], []
+    for i in range(N):
+        nt = int(rng.randint(1, 6))
+        xy = rng.uniform(0, 400, size=(nt, 2)); wh = rng.uniform(20, 200, size=(nt, 2))
+        tb = np.concatenate([xy, xy + wh], 1); tcs = rng.randint(0, C, size=nt)
+        targets.append([(tb[j], int(tcs[j])) for j in range(nt)])
+        pb, pc, ps = [], [], []
+        for j in range(nt):
+            for _ in range(int(rng.randint(1, 5))):
+                pb.append((tb[j] + rng.normal(0, 12, size=4)).astype(np.float32)); pc.append(np.int64(tcs[j]))
+                ps.append(np.float32(np.round(rng.uniform(0.05, 1), 2)))       # 96 distinct scores for ~12 000 predictions
+        predictions.append([pb, pc, ps])
+    th = [0.5, 0.75, 0.9]
+    got = metrics.mAP_table(predictions, targets, C, th)
+    want = orc.map_table(predictions, targets, C, th)
+    assert got.shape == (3, 2) and np.array_equal(got, want, equal_nan=True)
+    assert min(sum(1 for p in predictions for c in p[1] if int(c) == k) for k in range(C)) > 4096
