@@ -144,6 +144,7 @@ def make_loss_sets(cfg, B, device, nbuf, seed, logits=False):
     return anchors, sets
 
 
+MODE = {"exchange": "stream"}
 EXCHANGE = {"kind": None}   # how the loss scalars were summed over the ranks in the last time_loss_graph call
 PEER = {}                   # the PeerExchange shared by the benchmark's loss objects (its construction is a collective)
 
@@ -156,33 +157,41 @@ def time_loss_graph(anchors, sets, steps, warmup, device, world, from_logits=Fal
 
     from neuralnetworklibrary_b200.vision import SSD_loss, reduce_loss_scalars
 
-    # Several ranks: the 12-byte loss exchange is rn_peer_exchange, a kernel over peer-mapped memory INSIDE the step's graph
-    # (no NCCL call, no event pair per step); if symmetric memory is unavailable, the NCCL all-gather on a side stream.
+    # Several ranks: the 12-byte loss exchange.  MODE["exchange"]:
+    #   "stream" (default) rn_peer_exchange -- one kernel over peer-mapped memory -- on a side stream: step k+1's kernels do not
+    #            wait for step k's exchange (nothing on the GPU consumes the summed loss), so ranks may drift by a step
+    #            instead of synchronising every 0.36 ms;
+    #   "graph"  the same kernel INSIDE the step's CUDA graph (lowest latency to the global loss; every step then costs the
+    #            slowest rank's time);
+    #   "nccl"   all_gather_into_tensor on a side stream (also the fallback when symmetric memory is unavailable).
+    from neuralnetworklibrary_b200.vision import PeerExchange
     EXCHANGE["kind"] = "none (one rank)"
-    loss_fn = None
-    if world > 1:
-        try:
-            loss_fn = SSD_loss(global_batch=sets[0][0].shape[0] * world, from_logits=from_logits, distributed=True,
-                               peer_exchange=PEER["obj"] if PEER.get("obj") is not None else (False if PEER.get("failed") else True))
-            PEER["obj"] = loss_fn._exchange()
-            if PEER["obj"] is None:
-                raise RuntimeError("symmetric memory unavailable on some rank")
-            EXCHANGE["kind"] = "rn_peer_exchange: one kernel over peer-mapped (symmetric) memory inside the step's CUDA graph"
-        except Exception as exc:
-            loss_fn = None
-            PEER["failed"] = True
-            EXCHANGE["kind"] = "nccl all_gather_into_tensor on a side stream (peer-memory exchange unavailable: %s)" % type(exc).__name__
-    in_graph = loss_fn is not None
-    if loss_fn is None:
-        loss_fn = SSD_loss(global_batch=sets[0][0].shape[0] * world, from_logits=from_logits)
+    mode = MODE["exchange"] if world > 1 else "none"
+    px = None
+    if mode in ("stream", "graph"):
+        if "obj" not in PEER:
+            PEER["obj"] = PeerExchange.create()          # a collective; None on every rank if any rank failed
+        px = PEER["obj"]
+        if px is None:
+            mode = "nccl"
+    B_glob = sets[0][0].shape[0] * world
+    if mode == "graph":
+        loss_fn = SSD_loss(global_batch=B_glob, from_logits=from_logits, distributed=True, peer_exchange=px)
+        EXCHANGE["kind"] = "rn_peer_exchange: one kernel over peer-mapped (symmetric) memory inside the step's CUDA graph"
+    else:
+        loss_fn = SSD_loss(global_batch=B_glob, from_logits=from_logits)
+        if mode == "stream":
+            EXCHANGE["kind"] = "rn_peer_exchange: one kernel over peer-mapped (symmetric) memory on a side stream (pipelined with the next step)"
+        elif mode == "nccl":
+            EXCHANGE["kind"] = "nccl all_gather_into_tensor on a side stream"
+    in_graph = mode == "graph"
     caps = [loss_fn.capture([anchors, reg, clas], [gb, gc]) for clas, reg, gb, gc in sets]
 
-    # The 12-byte loss exchange runs on its own stream: step k+1's kernels do not wait for step k's all-gather
-    # (nothing on the GPU consumes the summed loss).  Each captured step owns its out3 buffer, and a step
-    # waits for the exchange that last read that buffer before overwriting it.
+    # Side-stream exchange: each captured step owns its out3 buffer, and a step waits for the exchange that last read that
+    # buffer before overwriting it.
     comm = torch.cuda.Stream(device=device) if world > 1 else None
     ready = [None] * len(caps)   # event: the exchange that read caps[i].out3 has finished
-    totals = [None] * len(caps)
+    totals = [torch.empty(3, dtype=torch.float32, device=device) for _ in caps]
 
     def step(k):
         i = k % len(caps)
@@ -198,7 +207,11 @@ def time_loss_graph(anchors, sets, steps, warmup, device, world, from_logits=Fal
         done.record(main)
         with torch.cuda.stream(comm):
             comm.wait_event(done)
-            totals[i] = reduce_loss_scalars(cap.out3)
+            if mode == "stream":
+                totals[i].copy_(cap.out3)
+                px(totals[i])
+            else:
+                totals[i] = reduce_loss_scalars(cap.out3)
             ready[i] = torch.cuda.Event()
             ready[i].record(comm)
         return totals[i]
@@ -383,7 +396,7 @@ def time_loss_e2e(cfg, B, steps, warmup, device, world, seed=1002):
     h_clas = torch.empty(clas_d.shape, dtype=torch.float32, pin_memory=True).copy_(clas_d)
     h_reg = torch.empty(reg_d.shape, dtype=torch.float32, pin_memory=True).copy_(reg_d)
     h_gb, h_gc = gb.pin_memory(), gc.pin_memory()
-    loss_fn = SSD_loss(distributed=world > 1, peer_exchange=PEER.get("obj") if PEER.get("obj") is not None else False)
+    loss_fn = SSD_loss(distributed=world > 1, peer_exchange=PEER.get("obj") or False)
     h2d = h_clas.numel() * 4 + h_reg.numel() * 4 + h_gb.numel() * 4 + h_gc.numel() * 8
     out = []
 
@@ -1036,9 +1049,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-b256", action="store_true", help="skip the BASELINE configs[4] extra (256 images over the ranks)")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle check of the first timed batch")
+    ap.add_argument("--exchange", default="stream", choices=["stream", "graph", "nccl"],
+                    help="multi-GPU loss exchange: rn_peer_exchange on a side stream / inside the step's graph, or NCCL")
     ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary-kernel measurements (section 8f rows 2-4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    MODE["exchange"] = args.exchange
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -134,7 +134,8 @@ int rn_loss(const float *clas, const float *reg, const float *gt_boxes, const in
  * reduction, i.e. SSD_loss.__call__ with its assignment (Vision.py:1474-1511, :1568-1644) and the autograd replay
  * (General/Learner.py:514).  Same inputs, outputs and numerics as the two separate calls; pos_thr / neg_thr are the
  * thresholds of match_anchors_objects (0.5 / 0.4).  npos_out [B] (positives per image) and matches_out [B,A] (the
- * rn_assign encoding; costs 4*A*B bytes of stores, meant for inspection and tests) may be NULL.
+ * rn_assign encoding; costs 4*A*B bytes of stores, meant for inspection and tests) may be NULL.  B == 0 (an empty image
+ * shard) only zeroes out3.
  * By default the call launches the kernels of rn_assign + rn_loss (background fill, one CTA per ground-truth box, the
  * streaming loss kernel, the final reduction; chained with programmatic dependent launch) -- the fastest variant measured
  * (profiles/r02_summary.md).  Two alternatives exist behind options, for generated anchors (anchors == NULL), M < 128 and

@@ -770,7 +770,12 @@ extern "C" int rn_loss_step(const float *clas, const float *reg, const float *gt
                             float *dclas, float *dreg, float *probs_out, float *out3, int32_t *npos_out,
                             int32_t *matches_out, void *state, size_t state_bytes, void *workspace, size_t workspace_bytes,
                             void *stream) {
-    if (B <= 0 || A <= 0 || C <= 0 || M < 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: B=%d A=%d C=%d M=%d", B, A, C, M);
+    if (B < 0 || A <= 0 || C <= 0 || M < 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: B=%d A=%d C=%d M=%d", B, A, C, M);
+    if (B == 0) {  // an empty image shard (more ranks than images): this rank's share of the three scalars is zero
+        if (!out3) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: null pointer");
+        cudaError_t e = cudaMemsetAsync(out3, 0, 3 * sizeof(float), (cudaStream_t)stream);
+        return e == cudaSuccess ? RN_OK : rn_set_error(RN_ERR_CUDA, "rn_loss_step memset: %s", cudaGetErrorString(e));
+    }
     if (!clas || !reg || !out3 || (M > 0 && (!gt_boxes || !gt_cats))) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: null pointer");
     if ((dclas == nullptr) != (dreg == nullptr))
         return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: dclas and dreg must both be given or both be NULL");

@@ -81,6 +81,9 @@ def _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, need_grad, bufs=Non
     out3 = bufs.get("out3")
     if out3 is None:
         out3 = torch.empty(3, dtype=torch.float32, device=dev)
+    if B == 0:   # an empty image shard: nothing to launch but the zeroing of the three scalars
+        npos = torch.empty((0,), dtype=torch.int32, device=dev)
+        matches = torch.empty((0, A), dtype=torch.int32, device=dev) if cfg.get("keep_matches") else None
     ws = bufs.get("ws")
     if ws is None:
         ws = _ws.get(lib.rn_loss_step_workspace_bytes(B, A, Cn), dev)
