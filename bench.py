@@ -237,7 +237,7 @@ def time_loss_graph(anchors, sets, steps, warmup, device, world, from_logits=Fal
         t = torch.tensor([total_ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    launches = caps[0].kernels_per_replay * steps
+    launches = caps[0].kernels_per_replay * steps + (steps if (world > 1 and mode == "stream") else 0)   # + rn_peer_exchange_kernel
     return total_ms, launches, float(out3[0].item())
 
 

@@ -408,11 +408,16 @@ rn_loss_final_kernel(const float2 *__restrict__ partials, const int32_t *__restr
         const int n = npos[b];  // issued ahead of the partial loads, consumed after them
         double cs = 0.0, rs = 0.0;
         const float2 *p = partials + (size_t)b * tiles;
-#pragma unroll 4
-        for (int t = lane; t < tiles; t += 32) {
-            const float2 v = p[t];
-            cs += (double)v.x;
-            rs += (double)v.y;
+#pragma unroll 1
+        for (int t0 = lane; t0 < tiles; t0 += 32 * 16) {  // 16 independent loads per lane in flight, fixed summation order
+            float2 v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (t0 + 32 * u < tiles) ? __ldg(p + t0 + 32 * u) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                cs += (double)v[u].x;
+                rs += (double)v[u].y;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

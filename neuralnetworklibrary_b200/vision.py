@@ -411,8 +411,12 @@ class SSD_loss(object):
     12-byte NCCL exchange; per-rank reg/clas gradients need no communication."""
 
     def __init__(self, beta=0.5, alpha=0.25, gamma=2.0, distributed=False, process_group=None, global_batch=None,
-                 from_logits=False, keep_probs=False, keep_matches=False, peer_exchange=False):
+                 from_logits=False, keep_probs=False, keep_matches=False, peer_exchange=False, validate_targets=False):
         self.beta, self.alpha, self.gamma = beta, alpha, gamma
+        # validate_targets: check on the host (one device->host sync per call) that every category is < C and raise the
+        # IndexError the reference raises at Vision.py:1593; off by default -- the kernels then treat such an anchor as
+        # positive without a class target
+        self.validate_targets = bool(validate_targets)
         # peer_exchange (with distributed=True): sum the loss scalars with rn_peer_exchange (a kernel over peer-mapped
         # memory on the step's own stream, part of the captured graph) instead of a NCCL all-gather; True creates the
         # PeerExchange on first use (a collective), or pass one.
@@ -439,6 +443,8 @@ class SSD_loss(object):
         if clas.dim() != 3 or reg.shape != clas.shape[:2] + (4,) or anchors.shape != (clas.shape[1], 4) \
                 or gt_cats.shape[0] != clas.shape[0]:
             raise ValueError("expected anchors [A,4], reg [bs,A,4], clas [bs,A,C], targets of the same batch size")
+        if self.validate_targets and gt_cats.numel() and int(gt_cats.max()) >= int(clas.shape[2]):
+            raise IndexError("category %d is out of bounds for %d classes" % (int(gt_cats.max()), int(clas.shape[2])))
         world = 1
         if self.distributed:
             import torch.distributed as dist

@@ -88,3 +88,25 @@ def test_other_anchor_sets(ratios, scales):
     assert np.array_equal(out["counts"], po["counts"])
     for i, n in enumerate(po["counts"]):
         assert np.array_equal(out["anchor_idx"][i, :n], po["anchor_idx"][i, :n])
+
+
+def test_empty_image_shard_and_target_validation():
+    """An empty shard (more ranks than images) contributes zero and empty gradients; validate_targets=True raises the
+    reference's IndexError for a category >= C (Vision.py:1593)."""
+    from neuralnetworklibrary_b200.retinanet import AnchorGenerator
+    from neuralnetworklibrary_b200.vision import SSD_loss
+    H, W, C, M = 96, 128, 8, 4
+    anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=dev()))
+    A = anchors.shape[0]
+    cd = torch.zeros((0, A, C), device=dev(), requires_grad=True)
+    rd = torch.zeros((0, A, 4), device=dev(), requires_grad=True)
+    f = SSD_loss(global_batch=5)
+    loss = f([anchors, rd, cd], [torch.zeros((0, M, 4), device=dev()), torch.zeros((0, M), dtype=torch.int64, device=dev())])
+    loss.backward()
+    assert loss.item() == 0.0 and f.reg_loss.item() == 0.0 and f.clas_loss.item() == 0.0
+    assert cd.grad.shape == (0, A, C) and rd.grad.shape == (0, A, 4)
+    gb, gc = syn.make_targets(2, M, H, W, C, seed=3)
+    clas, reg = syn.make_train_activations(2, A, C, seed=3)
+    gc[0, 0] = C
+    with pytest.raises(IndexError):
+        SSD_loss(validate_targets=True)([anchors, reg.to(dev()), clas.to(dev())], [gb.to(dev()), gc.to(dev())])
