@@ -340,8 +340,9 @@ class CapturedLevelLossStep(object):
 
 def reduce_loss_scalars(out3, group=None):
     """The one collective of the path: sums the three per-rank loss scalars over the image shards.
-    all_gather + one fixed-order sum over the rank axis (not all_reduce), so the result is bit-identical on
-    every rank and independent of the reduction algorithm NCCL picks.  12 bytes per rank: pure latency."""
+    all_gather + a sequential sum in rank order (not all_reduce, and not torch.sum, whose reduction tree is an
+    implementation detail), so the result is bit-identical on every rank, independent of the reduction algorithm NCCL
+    picks, and bit-identical to rn_peer_exchange.  12 bytes per rank: pure latency."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     out3 = out3.contiguous()
@@ -352,7 +353,10 @@ def reduce_loss_scalars(out3, group=None):
         parts = [torch.empty_like(out3) for _ in range(world)]
         dist.all_gather(parts, out3, group=group)
         gathered = torch.stack(parts)
-    return gathered.sum(dim=0)
+    total = gathered[0]
+    for r in range(1, world):
+        total = total + gathered[r]
+    return total
 
 
 class PeerExchange(object):
