@@ -634,21 +634,39 @@ rn_stage_images_kernel(const T *__restrict__ pixels, const int64_t *__restrict__
     const int n = C * Wp;
     const T *src = pixels + offsets[b] + (row_in ? (size_t)sy * cols * C : 0);
     const int lo = col_jit * C, hi = (col_jit + cols) * C;  // the image's columns in the padded row, in elements
-    for (int i = tid; i < n; i += 256) {
-        float v = 0.0f;
-        if (row_in && i >= lo && i < hi) {
-            const T raw = __ldg(src + (i - lo));
-            if (sizeof(T) == 1) {
-                v = (float)raw;
-                if (norm.on) {
-                    const int c = i % C;
-                    v = __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), norm.mean[c]), norm.std[c]);
+    if (sizeof(T) == 1) {
+        // bytes: zero the padding, then read the image's part of the row as aligned 32-bit words (4 pixels-channels per load;
+        // a word that straddles the ends of the row only contributes its bytes inside it -- it lies inside the same 4-byte
+        // aligned word of the allocation as a valid byte, so the read is always in bounds)
+        for (int i = tid; i < n; i += 256)
+            if (!row_in || i < lo || i >= hi) s_row[i] = 0.0f;
+        if (row_in) {
+            const int nb = hi - lo;
+            const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 3);
+            const uint32_t *w0 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(src) - mis);
+            const int words = (mis + nb + 3) >> 2;
+            for (int wi = tid; wi < words; wi += 256) {
+                const uint32_t w = __ldg(w0 + wi);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int idx = 4 * wi + k - mis;
+                    if (idx >= 0 && idx < nb) {
+                        float v = (float)((w >> (8 * k)) & 0xffu);
+                        if (norm.on) {
+                            const int c = (lo + idx) % C;
+                            v = __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), norm.mean[c]), norm.std[c]);
+                        }
+                        s_row[lo + idx] = v;
+                    }
                 }
-            } else {
-                v = (float)raw;
             }
         }
-        s_row[i] = v;
+    } else {
+        for (int i = tid; i < n; i += 256) {
+            float v = 0.0f;
+            if (row_in && i >= lo && i < hi) v = (float)__ldg(src + (i - lo));
+            s_row[i] = v;
+        }
     }
     __syncthreads();
     const int W4 = Wp >> 2;
