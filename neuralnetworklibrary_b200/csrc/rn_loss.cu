@@ -50,10 +50,23 @@ rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ R
     const int cta1 = min(nvec, cta0 + RN_LOSS_TILE * P.iters);
 
     if (tid < 32) rn_compact_gt(P.gt_boxes + (size_t)b * P.M, P.gt_cats + (size_t)b * P.M, P.M, s_box, nullptr, s_cat);
-    {   // Launched with PDL right behind rn_assign: pull this CTA's first sub-tile of `clas` (independent of the
-        // assignment) towards L2 while the assignment kernel drains, then wait for its matches / npos.
-        const float *first = P.clas + ((size_t)b * nvec + (size_t)cta0 + (size_t)tid * RN_LOSS_U) * V;
-        if (cta0 + tid * RN_LOSS_U < nvec) asm volatile("prefetch.global.L2 [%0];" ::"l"(first));
+    {   // Launched with PDL right behind rn_assign: while the assignment kernel (8 us of dependent latencies during which
+        // HBM idles) drains, pull this CTA's sub-tiles of `clas` (independent of the assignment) towards L2 -- one 128-byte
+        // line per thread and sub-tile -- then wait for its matches / npos.  P.prefetch: 1 = first sub-tile only,
+        // 2 = all of them (default), 3 = also those of the CTA that will take this CTA's place (first wave only).
+        const int linear = blockIdx.y * gridDim.x + blockIdx.x;
+        const int rounds = (P.prefetch >= 3 && linear < P.resident) ? 2 : 1;
+        for (int r = 0; r < rounds; ++r) {
+            const int lin = linear + r * P.resident;
+            const int pb = lin / (int)gridDim.x, px = lin - pb * (int)gridDim.x;
+            if (pb >= P.B) break;
+            const int p0 = px * (RN_LOSS_TILE * P.iters);
+            const int nsub = P.prefetch >= 2 ? P.iters : 1;
+            for (int it = 0; it < nsub; ++it) {
+                const int v = p0 + it * RN_LOSS_TILE + tid * RN_LOSS_U;
+                if (v < nvec) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.clas + ((size_t)pb * nvec + v) * V));
+            }
+        }
         rn_pdl_wait();
     }
 
@@ -251,6 +264,8 @@ int rn_loss_impl(bool logits, float *probs, const float *clas, const float *reg,
     P.npos = npos; P.table = reinterpret_cast<const float4 *>(anchors);
     P.dclas = dclas; P.dreg = dreg; P.probs = probs;
     P.B = B; P.A = A; P.C = C; P.CV = C / V; P.M = M; P.tiles = tiles; P.iters = rn_loss_iters(B, A, C);
+    P.prefetch = rn_opt(RN_OPT_LOSS_PREFETCH) > 0 ? rn_opt(RN_OPT_LOSS_PREFETCH) : 2;
+    P.resident = 148 * RN_LOSS_CTAS;
     P.a_pos = (float)alpha; P.a_neg = (float)(1.0 - alpha);  // Vision.py:1526
     P.gamma = (float)gamma;
     P.lo = (float)1e-4; P.hi = (float)(1.0 - 1e-4);          // Vision.py:1524

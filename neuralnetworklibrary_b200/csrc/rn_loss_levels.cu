@@ -19,14 +19,18 @@
 
 #include "rn_loss_math.cuh"
 
-// Tuning (measured on B200, COCO B=16, A/B runs inside one gpurun call next to the flat kernel; profiles/r01_summary.md):
+// Tuning (measured on B200, COCO B=16, A/B runs inside one gpurun call; profiles/r01_summary.md, profiles/r02_summary.md):
 // both variants wait for memory most of the time (stall_long_sb ~60 % of the samples), so the CTAs are small (128
-// threads: warps drift apart over a 40-class chunk and registers are only released per CTA) and every load of a block is
-// fenced ahead of its first consumer.  Probabilities: 8 planes in flight, 6 CTAs/SM (80 registers; 4 planes: 0.51 ms
-// instead of 0.42; double buffering at 2 CTAs/SM: no gain; 256-thread CTAs: 0.427).  Logits: 4 planes, 8 CTAs/SM
-// (64 registers, 0.487 ms; 8 planes at 6 CTAs/SM 0.53; 256-thread CTAs 0.54).  More class chunks per row tile are
-// slower (the CTA prologue -- ground-truth compaction, barrier, stride-K gather -- is paid per chunk): 1 chunk 0.416,
-// 5 chunks 0.463 ms.
+// threads: warps drift apart over a 40-class chunk and registers are only released per CTA), every load of a block is
+// fenced ahead of its first consumer, and each block's loads are followed by an L2 prefetch of the NEXT block of planes
+// (round 2: 0.419 -> 0.377 ms; look-ahead of 2/3/5/10 blocks is slower again).  With the prefetch in place a block of 4
+// planes is enough: probabilities 4 planes, 6 CTAs/SM 0.364 ms (8 planes/6 CTAs 0.385, 8/4 0.366, 4/8 0.370, 2/8 0.388);
+// logits 4 planes, 8 CTAs/SM 0.403 ms with the gradient chained through the sigmoid inside rn_focal_pair_neg (8/6 0.406,
+// 2/8 0.420, 8/4 0.429, 256-thread CTAs 0.410).  More class chunks per row tile are slower (the CTA prologue --
+// ground-truth compaction, barrier, stride-K gather -- is paid per chunk): 1 chunk 0.416, 5 chunks 0.463 ms.
+// The lambdas of the body are force-inlined: left to nvcc's inliner, whose decision depends on the rest of the module,
+// the same source produced class loops 10 % apart (two builds that differed only in the OTHER variant's macros).
+#define RN_LAMBDA_INLINE __attribute__((always_inline))
 #define RN_LVL_CHUNK_Q 8  // class chunks are multiples of this
 #ifndef RN_LVL_THREADS_PROB
 #define RN_LVL_THREADS_PROB 128
@@ -35,8 +39,11 @@
 #define RN_LVL_THREADS_LOGIT 128
 #endif
 #define RN_LVL_THREADS_MAX 256
+#ifndef RN_LVL_PF_DIST
+#define RN_LVL_PF_DIST 1  // blocks of look-ahead of the L2 prefetch (2, 3, 5, 10 measured slower, see load_block)
+#endif
 #ifndef RN_LVL_U_PROB
-#define RN_LVL_U_PROB 8
+#define RN_LVL_U_PROB 4
 #endif
 #ifndef RN_LVL_CTAS_PROB
 #define RN_LVL_CTAS_PROB 6
@@ -64,6 +71,7 @@ struct RnLvlParams {
     int V[RN_NUM_LEVELS];         // cells per thread (4, 2 or 1)
     int tile0[RN_NUM_LEVELS + 1]; // first row-tile of each level in the per-image tile list
     int cchunk, nchunks;          // classes per CTA, chunks per row-tile
+    int prefetch;                 // L2 prefetch RN_LVL_PF_DIST blocks of class planes ahead
     float a_pos, a_neg, gamma, lo, hi;
     float wc_over_bs, wr_over_bs;
 };
@@ -135,16 +143,34 @@ __device__ __forceinline__ void rn_lvl_body(const RnLvlParams &P, const RnGeom &
     // The first block of class planes is requested before anything else: it does not depend on the ground truth,
     // on the assignment kernel this launch overlaps with (PDL) or on the CTA barrier below.
     RnLv<V> xv[U];
-    auto load_block = [&](RnLv<V>(&dst)[U], int c0) {
+    // L2 prefetch of the block AFTER the one being loaded (one request per 128-byte line of the warp's contiguous run, plus the
+    // warp's last lane for a run that is not line aligned): the kernel waits on memory most of the time (long_scoreboard 6.7
+    // per issue), and a block's planes are ~2 us of work away -- the next block's loads then hit L2.
+    const int lane_pf = threadIdx.x & 31;
+    const bool pf_lane = ((lane_pf * V * 4) % 128 == 0) || lane_pf == 31;
+    auto load_block = [&](RnLv<V>(&dst)[U], int c0) RN_LAMBDA_INLINE {
         const float *xq = xp + (size_t)c0 * Pl;
 #pragma unroll
         for (int u = 0; u < U; ++u) dst[u].load(xq + u * Pl);
+        if (P.prefetch && pf_lane && c0 + (RN_LVL_PF_DIST + 1) * U <= c_end) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) asm volatile("prefetch.global.L2 [%0];" ::"l"(xq + (size_t)(RN_LVL_PF_DIST * U + u) * Pl));
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) dst[u].keep();  // every load of the block is issued before its first consumer
     };
     int c = c_begin;
     bool have = valid && (c + U <= c_end);
-    if (have) load_block(xv, c);
+    if (have) {
+        load_block(xv, c);
+        // the blocks between the first one and the look-ahead distance
+#pragma unroll
+        for (int d = 1; d < RN_LVL_PF_DIST; ++d)
+            if (P.prefetch && pf_lane && c + (d + 1) * U <= c_end) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) asm volatile("prefetch.global.L2 [%0];" ::"l"(xp + (size_t)(c + d * U + u) * Pl));
+            }
+    }
 
     if (threadIdx.x < 32) rn_compact_gt(P.gt_boxes + (size_t)b * P.M, P.gt_cats + (size_t)b * P.M, P.M, s_box, nullptr, s_cat);
     rn_pdl_wait();  // launched with PDL right behind rn_assign: wait for its matches / npos
@@ -158,7 +184,7 @@ __device__ __forceinline__ void rn_lvl_body(const RnLvlParams &P, const RnGeom &
     const float ga_pos = P.a_pos * gl;
     float *dp = GRAD ? P.dclas[l] + plane0 * Pl + p : nullptr;
     float *pp = (LOGITS && P.probs[l]) ? P.probs[l] + plane0 * Pl + p : nullptr;
-    auto next_block = [&]() {
+    auto next_block = [&]() RN_LAMBDA_INLINE {
         c += U;
         have = c + U <= c_end;
         if (have) load_block(xv, c);
@@ -180,16 +206,12 @@ __device__ __forceinline__ void rn_lvl_body(const RnLvlParams &P, const RnGeom &
             }
         }
         // two background elements: probabilities (in place), gradients, packed sum
-        auto two = [&](float &y0, float &y1, float &g0, float &g1, rn_f2 ga, rn_f2 &acc) {
+        auto two = [&](float &y0, float &y1, float &g0, float &g1, rn_f2 ga, rn_f2 &acc) RN_LAMBDA_INLINE {
             if (LOGITS) rn_sigmoid_pair(y0, y1, y0, y1);
             g0 = g1 = 0.0f;
-            rn_focal_pair_neg<GRAD>(y0, y1, P.lo, P.hi, ga, acc, g0, g1);
-            if (LOGITS && GRAD) {  // sigmoid backward: grad * (1 - y) * y
-                g0 = (g0 * (1.0f - y0)) * y0;
-                g1 = (g1 * (1.0f - y1)) * y1;
-            }
+            rn_focal_pair_neg<GRAD, LOGITS>(y0, y1, P.lo, P.hi, ga, acc, g0, g1);  // LOGITS: chained through the sigmoid
         };
-        auto plane = [&](RnLv<V> &x, size_t off, rn_f2 *acc) {  // one class plane, V >= 2
+        auto plane = [&](RnLv<V> &x, size_t off, rn_f2 *acc) RN_LAMBDA_INLINE {  // one class plane, V >= 2
             RnLv<V> gv;
 #pragma unroll
             for (int h = 0; h < NPK; ++h) two(x.at(2 * h), x.at((2 * h + 1) % V), gv.at(2 * h), gv.at((2 * h + 1) % V), ga2[h], acc[h]);
@@ -275,7 +297,7 @@ __device__ __forceinline__ void rn_lvl_body(const RnLvlParams &P, const RnGeom &
         }
     } else {
         // general gamma: scalar element math with a run-time target
-        auto elems = [&](RnLv<V> &x, int cls, size_t off) {
+        auto elems = [&](RnLv<V> &x, int cls, size_t off) RN_LAMBDA_INLINE {
             RnLv<V> gv;
 #pragma unroll
             for (int e = 0; e < V; ++e) {
@@ -516,6 +538,7 @@ extern "C" int rn_loss_levels(const float *const *clas_levels, const float *cons
     P.matches = matches; P.npos = npos;
     P.B = B; P.A = pl.A; P.C = C; P.M = M; P.K = K;
     P.cchunk = pl.cchunk; P.nchunks = pl.nchunks;
+    P.prefetch = rn_opt(RN_OPT_LOSS_PREFETCH) != 1;  // option value 1 = no look-ahead (A/B measurements)
     P.a_pos = (float)alpha; P.a_neg = (float)(1.0 - alpha);  // Vision.py:1526
     P.gamma = (float)gamma;
     P.lo = (float)1e-4; P.hi = (float)(1.0 - 1e-4);          // Vision.py:1524

@@ -184,7 +184,7 @@ struct RnLossParams {
     float *dreg;
     float *probs;     // LOGITS only, may be NULL: sigmoid(logits) as used by the kernel (for checking / reuse)
     float *partials;  // [B][tiles][2] : {sum of focal terms, sum of smooth-L1 terms}
-    int B, A, C, CV, M, tiles, iters;
+    int B, A, C, CV, M, tiles, iters, prefetch, resident;
     float a_pos, a_neg, gamma, lo, hi;
     float wc_over_bs, wr_over_bs;  // beta / B_global, (1-beta) / B_global   (Vision.py:1644)
 };

@@ -1,5 +1,5 @@
 """Developer micro-benchmarks (not the contract bench): times selected pieces of bench.py in isolation.
-usage: python profiles/dev_bench.py levels|levels_logits|pascal|postproc|logits [steps]"""
+usage: python profiles/dev_bench.py levels|levels_logits|pascal|postproc|logits [steps] [option=value ...]   (rn_set_option)"""
 import json
 import os
 import sys
@@ -13,6 +13,10 @@ import bench  # noqa: E402
 what = sys.argv[1].split(",") if len(sys.argv) > 1 else ["levels"]
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 dev = torch.device("cuda:0")
+from neuralnetworklibrary_b200 import _lib  # noqa: E402
+for kv in sys.argv[3:]:
+    _k, _v = kv.split("=")
+    _lib.check(_lib.load().rn_set_option(_k.encode(), int(_v)))
 torch.cuda.set_device(dev)
 peak = bench.peaks()[0]
 out = {}
@@ -41,4 +45,4 @@ for w in what:
     elif w == "postproc":
         pms, pwall, ncand, nkept, _ = bench.time_postproc(COCO, 64, steps, 3, dev)
         out[w] = {"ms": pms / steps, "wall_ms": pwall / steps, "frac": bench.loss_bytes(64, A, 80, grad=False) / (pms / steps * 1e-3) / 1e9 / peak}
-print(json.dumps(out))
+print(" ".join(sys.argv[3:]), json.dumps(out))
