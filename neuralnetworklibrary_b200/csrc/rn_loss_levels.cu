@@ -26,8 +26,9 @@
 // (round 2: 0.419 -> 0.377 ms; look-ahead of 2/3/5/10 blocks is slower again).  With the prefetch in place a block of 4
 // planes is enough: probabilities 4 planes, 6 CTAs/SM 0.364 ms (8 planes/6 CTAs 0.385, 8/4 0.366, 4/8 0.370, 2/8 0.388);
 // logits 4 planes, 8 CTAs/SM 0.403 ms with the gradient chained through the sigmoid inside rn_focal_pair_neg (8/6 0.406,
-// 2/8 0.420, 8/4 0.429, 256-thread CTAs 0.410).  More class chunks per row tile are slower (the CTA prologue --
-// ground-truth compaction, barrier, stride-K gather -- is paid per chunk): 1 chunk 0.416, 5 chunks 0.463 ms.
+// 2/8 0.420, 8/4 0.429, 256-thread CTAs 0.410).  A second register buffer per thread (RN_LVL_DB=1: the next block's loads
+// issued ahead of the current block's arithmetic) does not help on top of the L2 prefetch: 0.363 vs 0.357 ms
+// (probabilities), 0.400-0.465 vs 0.384 ms (logits, which then spill or lose occupancy).
 // The lambdas of the body are force-inlined: left to nvcc's inliner, whose decision depends on the rest of the module,
 // the same source produced class loops 10 % apart (two builds that differed only in the OTHER variant's macros).
 #define RN_LAMBDA_INLINE __attribute__((always_inline))
@@ -41,6 +42,9 @@
 #define RN_LVL_THREADS_MAX 256
 #ifndef RN_LVL_PF_DIST
 #define RN_LVL_PF_DIST 1  // blocks of look-ahead of the L2 prefetch (2, 3, 5, 10 measured slower, see load_block)
+#endif
+#ifndef RN_LVL_DB
+#define RN_LVL_DB 0  // 1: two register buffers per thread (measured: see the tuning note)
 #endif
 #ifndef RN_LVL_U_PROB
 #define RN_LVL_U_PROB 4
@@ -218,20 +222,18 @@ __device__ __forceinline__ void rn_lvl_body(const RnLvlParams &P, const RnGeom &
             if (LOGITS && pp) x.store(pp + off);
             if (GRAD) gv.store(dp + off);
         };
-#pragma unroll 1
-        while (have) {
-            const size_t off = (size_t)c * Pl;
+        auto block = [&](RnLv<V>(&xb)[U], size_t off) RN_LAMBDA_INLINE {  // U class planes held in registers
             if (V >= 2) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) plane(xv[u], off + u * Pl, acc2);
+                for (int u = 0; u < U; ++u) plane(xb[u], off + u * Pl, acc2);
             } else {  // V == 1: pair two class planes of the same cell
 #pragma unroll
                 for (int u = 0; u < U; u += 2) {
                     RnLv<V> g0, g1;
-                    two(xv[u].at(0), xv[u + 1].at(0), g0.at(0), g1.at(0), ga2[0], acc2[0]);
+                    two(xb[u].at(0), xb[u + 1].at(0), g0.at(0), g1.at(0), ga2[0], acc2[0]);
                     if (LOGITS && pp) {
-                        xv[u].store(pp + off + u * Pl);
-                        xv[u + 1].store(pp + off + (u + 1) * Pl);
+                        xb[u].store(pp + off + u * Pl);
+                        xb[u + 1].store(pp + off + (u + 1) * Pl);
                     }
                     if (GRAD) {
                         g0.store(dp + off + u * Pl);
@@ -239,7 +241,30 @@ __device__ __forceinline__ void rn_lvl_body(const RnLvlParams &P, const RnGeom &
                     }
                 }
             }
-            next_block();
+        };
+        if constexpr (RN_LVL_DB) {
+            // register double buffering: the next block's loads are issued before the current block's arithmetic
+            RnLv<V> xw[U];
+            auto step = [&](RnLv<V>(&cur)[U], RnLv<V>(&nxt)[U]) RN_LAMBDA_INLINE {
+                const size_t off = (size_t)c * Pl;
+                const bool more = c + 2 * U <= c_end;
+                if (more) load_block(nxt, c + U);
+                block(cur, off);
+                c += U;
+                have = more;
+            };
+#pragma unroll 1
+            while (have) {
+                step(xv, xw);
+                if (!have) break;
+                step(xw, xv);
+            }
+        } else {
+#pragma unroll 1
+            while (have) {
+                block(xv, (size_t)c * Pl);
+                next_block();
+            }
         }
         float rem1 = 0.0f;  // V == 1 only: remainder planes of the single cell
 #pragma unroll 1
@@ -459,10 +484,13 @@ static void rn_lvl_plan(RnLvlPlan *pl, int B, int H, int W, int K, int C, bool l
         pl->tile0[l + 1] = pl->tile0[l] + (K * P + per_tile - 1) / per_tile;
     }
     // classes per CTA: as many as possible (the stride-K gather of the assignments and the prologue are paid once
-    // per CTA) while the grid keeps >= ~8 waves of 148 SMs x 3 resident CTAs; chunks are balanced multiples of RN_LVL_CHUNK_Q.
+    // per CTA) while the grid keeps >= ~8 waves of 148 SMs x the resident CTAs, but never fewer than 40 classes per chunk
+    // (Pascal, C = 20, B = 32: 1 chunk 65 us, 2 chunks 70 us, 3 chunks 74 us; COCO, C = 80, B = 16: 1 chunk 0.371 ms,
+    // 2 chunks 0.357, 3 chunks 0.359, 5 chunks 0.371); chunks are balanced multiples of RN_LVL_CHUNK_Q.
     const int blocks = (C + RN_LVL_CHUNK_Q - 1) / RN_LVL_CHUNK_Q;
+    const int nch_max = max(1, blocks / 5);
     int nch = 1;
-    while (nch < blocks && (long long)B * pl->tile0[RN_NUM_LEVELS] * nch < 8LL * 148 * ctas) ++nch;
+    while (nch < nch_max && (long long)B * pl->tile0[RN_NUM_LEVELS] * nch < 8LL * 148 * ctas) ++nch;
     if (rn_opt(RN_OPT_LVL_NCHUNKS) > 0) nch = max(1, min(blocks, rn_opt(RN_OPT_LVL_NCHUNKS)));  // tuning override (rn_set_option)
     int cchunk = ((blocks + nch - 1) / nch) * RN_LVL_CHUNK_Q;
     if (cchunk > C) cchunk = C;
