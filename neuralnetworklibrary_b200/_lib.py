@@ -24,7 +24,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "-fmad=false",  # never contract a*b+c behind our back; fused ops are spelled fmaf() explicitly
-    "-split-compile", "0",  # build-time only: ptxas works on the kernels of a translation unit in parallel
+    # no -split-compile: with it, identical command lines produced different SASS from run to run (the partition of a
+    # translation unit depends on thread timing) and the level-tensor kernels came out 2-3 % apart (profiles/r02_summary.md)
     "-Xcompiler", "-fPIC",
 ]
 

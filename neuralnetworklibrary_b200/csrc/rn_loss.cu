@@ -24,6 +24,9 @@
 #ifndef RN_LOSS_CTAS
 #define RN_LOSS_CTAS 3
 #endif
+#ifndef RN_LOSS_CTAS_LOGIT
+#define RN_LOSS_CTAS_LOGIT 3
+#endif
 
 // V: floats per vector (4 when C % 4 == 0, else 1).  CVT: compile-time vectors per row (0 = runtime).
 // Each CTA handles P.iters consecutive sub-tiles of one image (the prologue -- ground-truth compaction,
@@ -33,7 +36,7 @@
 // occupancy to two CTAs per SM and the kernel from 370 us to 419 us (profiles/r01_summary.md).
 // MT: where the assignment comes from (RnMatchI32: rn_assign's int32 matches; RnMatchU8: the byte map of rn_loss_step).
 template <int V, int CVT, bool G2, bool GRAD, bool LOGITS, typename MT>
-__global__ void __launch_bounds__(RN_THREADS, RN_LOSS_CTAS)
+__global__ void __launch_bounds__(RN_THREADS, LOGITS ? RN_LOSS_CTAS_LOGIT : RN_LOSS_CTAS)
 rn_loss_kernel(const __grid_constant__ RnLossParams P, const __grid_constant__ RnGeom g) {
     extern __shared__ __align__(16) unsigned char smem[];
     // layout: gt boxes float4[M] | gt cats int[M]

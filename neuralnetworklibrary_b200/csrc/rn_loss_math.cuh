@@ -97,30 +97,43 @@ __device__ __forceinline__ rn_f2 rn_add2(rn_f2 a, rn_f2 b) {
 }
 __device__ __forceinline__ rn_f2 rn_splat(float a) { return rn_pack(a, a); }
 
+#ifndef RN_SIGMOID_NEWTON
+#define RN_SIGMOID_NEWTON 0  // 1: refine MUFU.RCP by one Newton step (3 more packed instructions per pair)
+#endif
 // sigmoid of two logits, arithmetic packed two-wide: 2^(z * -log2 e) with the product's rounding error
-// carried in a correction term, MUFU.EX2, 1 + e, MUFU.RCP refined by one Newton step.  Within ~5 ulp of the
-// correctly rounded value (MUFU.EX2 itself is a 2-ulp approximation); ~5 issue slots per element instead of
-// the ~17 of expf + an IEEE divide.
+// carried in a correction term, MUFU.EX2, 1 + e, MUFU.RCP.  Within 6 ulp of the correctly rounded value (MUFU.EX2 is
+// a 2-ulp approximation, MUFU.RCP a 1-ulp one; tests/test_gpu_assign_loss.py checks the bound); ~5 issue slots per
+// element instead of the ~17 of expf + an IEEE divide.  The logits kernels are limited by instruction issue (issue
+// active 69 %, math-pipe throttle and not-selected stalls 2.1 / 2.2 per issue, profiles/r02_summary.md): leaving out the
+// Newton refinement of the reciprocal (0.5 ulp) takes the flat logits step from 0.397 to 0.380 ms and the level-tensor one
+// from 0.402 to 0.382 ms.
 __device__ __forceinline__ void rn_sigmoid_pair(float z0, float z1, float &y0, float &y1) {
+    // Signs are folded into the constants so that no negation (two LOP3 per packed value) is needed:
+    //   t_hi = z * c,  c = float32(-log2 e);   s = -(z*c - t_hi) - z*c_lo = -(t_lo)   (two FFMA2 with -c, -c_lo)
+    //   2^(t_hi + t_lo) = eb + (eb * -ln 2) * s
     const rn_f2 z = rn_pack(z0, z1);
-    const rn_f2 c_hi = rn_splat(-1.4426950216293335f);       // float32(-log2 e)
-    const rn_f2 t_hi = rn_mul2(z, c_hi);
-    rn_f2 t_lo = rn_fma2(z, c_hi, t_hi ^ 0x8000000080000000ull);          // exact residual of the product
-    t_lo = rn_fma2(z, rn_splat(-1.925963033500011e-08f), t_lo);           // + z * (-log2 e - float32(-log2 e))
+    const rn_f2 t_hi = rn_mul2(z, rn_splat(-1.4426950216293335f));
+    rn_f2 s = rn_fma2(z, rn_splat(1.4426950216293335f), t_hi);            // -(exact residual of the product)
+    s = rn_fma2(z, rn_splat(1.925963033500011e-08f), s);                  // - z * (-log2 e - float32(-log2 e))
     float a0, a1;
     rn_unpack(t_hi, a0, a1);
     float e0, e1;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
     const rn_f2 eb = rn_pack(e0, e1);
-    const rn_f2 e = rn_fma2(rn_mul2(eb, rn_splat(0.6931471805599453f)), t_lo, eb);  // 2^(t_hi + t_lo)
+    const rn_f2 e = rn_fma2(rn_mul2(eb, rn_splat(-0.6931471805599453f)), s, eb);  // 2^(t_hi + t_lo)
     const rn_f2 one = rn_splat(1.0f);
     const rn_f2 d = rn_add2(e, one);
     float d0, d1;
     rn_unpack(d, d0, d1);
     const rn_f2 r0 = rn_pack(rn_rcp_approx(d0), rn_rcp_approx(d1));
-    const rn_f2 err = rn_fma2(d ^ 0x8000000080000000ull, r0, one);       // 1 - d * r0
+#if RN_SIGMOID_NEWTON
+    const rn_f2 dn = rn_fma2(e, rn_splat(-1.0f), rn_splat(-1.0f));        // -(1 + e), same rounding as d
+    const rn_f2 err = rn_fma2(dn, r0, one);                               // 1 - d * r0
     rn_unpack(rn_fma2(r0, err, r0), y0, y1);
+#else
+    rn_unpack(r0, y0, y1);
+#endif
 }
 
 // Two background (target 0) class elements with gamma == 2: same mathematics as
