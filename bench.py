@@ -149,6 +149,9 @@ EXCHANGE = {"kind": None}   # how the loss scalars were summed over the ranks in
 PEER = {}                   # the PeerExchange shared by the benchmark's loss objects (its construction is a collective)
 
 
+RANK_MS = {}   # time_loss_graph: per-rank ms/step of its last multi-rank call
+
+
 def time_loss_graph(anchors, sets, steps, warmup, device, world, from_logits=False):
     """`steps` replays of the captured step (assign kernel + fused loss fwd/bwd/reduction kernel),
     rotating over the input sets; with several ranks each step ends with the 12-byte loss exchange."""
@@ -235,6 +238,9 @@ def time_loss_graph(anchors, sets, steps, warmup, device, world, from_logits=Fal
     total_ms = t0.elapsed_time(t1)
     if world > 1:
         t = torch.tensor([total_ms], device=device)
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        RANK_MS["last"] = [round(float(v.item()) / steps, 4) for v in every]   # each rank's own device time per step
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     launches = caps[0].kernels_per_replay * steps + (steps if (world > 1 and mode == "stream") else 0)   # + rn_peer_exchange_kernel
@@ -824,6 +830,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     total_ms, launches, last_loss = time_loss_graph(anchors, sets, args.steps, args.warmup, device, world)
+    rank_ms = RANK_MS.get("last")
     exchange_kind = EXCHANGE["kind"]
     clocks = sampler.stop() if rank == 0 else None
     images = B * world * args.steps
@@ -870,6 +877,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(total_ms / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "loss_exchange": exchange_kind,
+            "ms_per_step_by_rank": rank_ms,   # N > 1: each rank's own device time; ms_per_step is their maximum
             "config": {"workload": "coco_loss_fwd_bwd: assign + focal/smooth-L1 fwd+bwd, B=%d/GPU, 800x1344, A=%d, C=80, M=20"
                                    % (B, A), "global_batch": B * world, "parallelism": "image-sharded dp%d" % world,
                        "l2": "inputs (1.1 GB/step, 2 rotating sets) larger than the 126 MB L2",
@@ -925,11 +933,14 @@ def run_ours(args):
             pA = pan.shape[0]
             psteps = max(args.steps, 40)
             pt, _, _ = time_loss_graph(pan, psets, psteps, args.warmup, device, 1)
-            _, pk, _ = time_loss_eager(pan, psets, args.steps, args.warmup, device)
+            pe, pk, _ = time_loss_eager(pan, psets, args.steps, args.warmup, device)
             del psets
             line["pascal"] = {"workload": "pascal_loss_fwd_bwd B=32 512x512 C=20 M=10 (BASELINE configs[1])",
                               "images_per_s": round(32 * psteps / (pt * 1e-3), 1), "ms_per_step": round(pt / psteps, 4),
                               "rn_loss_ms": round(pk, 4),
+                              "eager_ms_per_step": round(pe / args.steps, 4),
+                              "eager_note": "SSD_loss()(...) + backward() call by call: at this size the step is bound by the "
+                                            "Python issue time of the autograd Function, not by the device",
                               "roofline_frac_rn_loss": round(loss_bytes(32, pA, 20) / (pk * 1e-3) / 1e9 / peak, 4),
                               "roofline_frac_whole_step": round(loss_bytes(32, pA, 20) * psteps / (pt * 1e-3) / 1e9 / peak, 4)}
         except Exception as exc:

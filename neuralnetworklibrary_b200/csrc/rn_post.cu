@@ -421,7 +421,8 @@ __device__ __forceinline__ int rn_block_excl_scan_1024(int v, int *s_warp /*[32]
 __global__ void __launch_bounds__(RN_SEL_THREADS)
 rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t *__restrict__ counts, int cap,
                       const int32_t *__restrict__ seg_off /* NULL: image b owns keys[b*cap ..); else keys[seg_off[b] .. seg_off[b+1]) */,
-                      int top_k, unsigned long long *__restrict__ sel, int32_t *__restrict__ nsel) {
+                      int top_k, unsigned score_lo, unsigned score_hi /* range of the keys' upper 32 bits when known, else 0, 0 */,
+                      unsigned long long *__restrict__ sel, int32_t *__restrict__ nsel) {
     __shared__ unsigned long long s_keys[RN_SORT_N];
     __shared__ int s_hist[RN_BINS];
     __shared__ int s_warp[32];
@@ -441,10 +442,68 @@ rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t
     int limit = 1024;
     while (limit < K) limit <<= 1;
     int total;  // keys staged in s_keys
+    // rank search over s_hist (bins in descending order, thread t owns bins 2t and 2t+1 from the top): the bin that holds the
+    // need-th largest key, the number of keys above it and its own count -> s_digit / s_above / s_bincnt
+    auto find_bin = [&](int need) {
+        const int d0 = RN_BINS - 1 - 2 * tid, d1 = d0 - 1;
+        const int c0 = s_hist[d0], c1 = s_hist[d1];
+        const int ex = rn_block_excl_scan_1024(c0 + c1, s_warp);
+        if (ex < need && need <= ex + c0) {
+            s_digit = d0; s_above = ex; s_bincnt = c0;
+        } else if (ex + c0 < need && need <= ex + c0 + c1) {
+            s_digit = d1; s_above = ex + c0; s_bincnt = c1;
+        }
+        __syncthreads();
+    };
+    // every key of the image, four independent loads per thread in flight (a pass is a chain of L2 round trips otherwise:
+    // 17 k keys per image over 1024 threads = 17 dependent-latency iterations per pass)
+    auto for_each_key = [&](auto &&fn) {
+        for (int i0 = tid; i0 < n; i0 += 4 * RN_SEL_THREADS) {
+            unsigned long long k4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) k4[u] = (i0 + u * RN_SEL_THREADS < n) ? __ldg(kb + i0 + u * RN_SEL_THREADS) : 0ull;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i0 + u * RN_SEL_THREADS < n) fn(k4[u]);
+        }
+    };
+    bool staged = false;
     if (n <= limit) {
         for (int i = tid; i < n; i += RN_SEL_THREADS) s_keys[i] = kb[i];
         total = n;
-    } else {
+        staged = true;
+    } else if (score_hi > score_lo) {
+        // Fast path when the caller knows the range of the keys' upper halves (post-processing: the sortable bits of the
+        // score threshold and of 1.0): ONE histogram over a monotone binning of that range -- 2048 bins across
+        // [score_lo, score_hi], values outside clamp into the end bins -- instead of radix digits from bit 63 down, whose
+        // first 11 bits (sign, exponent, two mantissa bits) put 17 k scores into ~20 bins: three passes and 17 k
+        // shared-memory atomics on a handful of addresses.  Any monotone binning keeps the selection exact; if the bin of the
+        // K-th key does not narrow the candidates to `limit`, the generic passes below start over.
+        const unsigned range = score_hi - score_lo;
+        const int sh = max(0, 32 - __clz(range) - RN_DIGIT_BITS);
+        auto bin_of = [&](unsigned long long k) {
+            const unsigned sc = (unsigned)(k >> 32);
+            const unsigned v = sc > score_lo ? sc - score_lo : 0u;
+            return (int)min(v >> sh, (unsigned)(RN_BINS - 1));
+        };
+        for (int i = tid; i < RN_BINS; i += RN_SEL_THREADS) s_hist[i] = 0;
+        __syncthreads();
+        for_each_key([&](unsigned long long k) { atomicAdd(&s_hist[bin_of(k)], 1); });
+        __syncthreads();
+        find_bin(K);
+        const int digit = s_digit, fits = s_above + s_bincnt <= limit;
+        if (tid == 0) s_n = 0;
+        __syncthreads();
+        if (fits) {
+            for_each_key([&](unsigned long long k) {
+                if (bin_of(k) >= digit) s_keys[atomicAdd(&s_n, 1)] = k;
+            });
+            __syncthreads();
+            total = s_n;
+            staged = true;
+        }
+    }
+    if (!staged) {
         // radix select from the most significant digit down until (#certain + #in-bin) fits
         unsigned long long prefix = 0;
         int done = 0, need = K, above_total = 0;
@@ -453,30 +512,11 @@ rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t
             const int shift = 64 - done - db;
             for (int i = tid; i < RN_BINS; i += RN_SEL_THREADS) s_hist[i] = 0;
             __syncthreads();
-            // four independent key loads per thread in flight (the pass is a chain of L2 round trips otherwise: 17 k keys per
-            // image over 1024 threads = 17 dependent-latency iterations per pass, ~30 us for the kernel)
-            for (int i0 = tid; i0 < n; i0 += 4 * RN_SEL_THREADS) {
-                unsigned long long k4[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) k4[u] = (i0 + u * RN_SEL_THREADS < n) ? __ldg(kb + i0 + u * RN_SEL_THREADS) : 0ull;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const unsigned long long k = k4[u];
-                    if (i0 + u * RN_SEL_THREADS < n && (done == 0 || (k >> (64 - done)) == prefix))
-                        atomicAdd(&s_hist[(int)((k >> shift) & ((1u << db) - 1u))], 1);
-                }
-            }
+            for_each_key([&](unsigned long long k) {
+                if (done == 0 || (k >> (64 - done)) == prefix) atomicAdd(&s_hist[(int)((k >> shift) & ((1u << db) - 1u))], 1);
+            });
             __syncthreads();
-            // bins in descending digit order: thread t owns ranks 2t and 2t+1
-            const int d0 = RN_BINS - 1 - 2 * tid, d1 = d0 - 1;
-            const int c0 = s_hist[d0], c1 = s_hist[d1];
-            const int ex = rn_block_excl_scan_1024(c0 + c1, s_warp);
-            if (ex < need && need <= ex + c0) {
-                s_digit = d0; s_above = ex; s_bincnt = c0;
-            } else if (ex + c0 < need && need <= ex + c0 + c1) {
-                s_digit = d1; s_above = ex + c0; s_bincnt = c1;
-            }
-            __syncthreads();
+            find_bin(need);
             above_total += s_above;
             need -= s_above;
             prefix = (prefix << db) | (unsigned long long)s_digit;
@@ -487,20 +527,13 @@ rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t
         }
         if (tid == 0) s_n = 0;
         __syncthreads();
-        for (int i0 = tid; i0 < n; i0 += 4 * RN_SEL_THREADS) {
-            unsigned long long k4[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) k4[u] = (i0 + u * RN_SEL_THREADS < n) ? __ldg(kb + i0 + u * RN_SEL_THREADS) : 0ull;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const unsigned long long k = k4[u];
-                const unsigned long long top = (done == 64) ? k : (k >> (64 - done));
-                if (i0 + u * RN_SEL_THREADS < n && top >= prefix) {
-                    const int pos = atomicAdd(&s_n, 1);
-                    if (pos < RN_SORT_N) s_keys[pos] = k;
-                }
+        for_each_key([&](unsigned long long k) {
+            const unsigned long long top = (done == 64) ? k : (k >> (64 - done));
+            if (top >= prefix) {
+                const int pos = atomicAdd(&s_n, 1);
+                if (pos < RN_SORT_N) s_keys[pos] = k;
             }
-        }
+        });
         __syncthreads();
         total = min(s_n, RN_SORT_N);
     }
@@ -508,6 +541,34 @@ rn_post_select_kernel(const unsigned long long *__restrict__ keys, const int32_t
     while (P < total) P <<= 1;
     for (int i = total + tid; i < P; i += RN_SEL_THREADS) s_keys[i] = 0ull;  // sorts to the end
     __syncthreads();
+    if (P <= RN_SEL_THREADS) {
+        // One key per thread, held in a register: the compare-exchange steps with a partner inside the warp (j < 32) are two
+        // shuffles and no barrier; only the 15 of the 55 steps of a 1024-key network whose partner lives in another warp go
+        // through shared memory (double-buffered: one barrier per step).  The network in shared memory alone was 46 % of the
+        // kernel's stall samples (profiles/r02_summary.md).
+        unsigned long long *s_alt = s_keys + RN_SEL_THREADS;   // second buffer (RN_SORT_N >= 2 * RN_SEL_THREADS)
+        unsigned long long x = tid < P ? s_keys[tid] : 0ull;
+        int buf = 1;  // s_keys holds the input: the first cross-warp step writes s_alt
+        for (int k = 2; k <= P; k <<= 1) {
+            const bool desc = (tid & k) == 0;
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                unsigned long long y;
+                if (j >= 32) {
+                    unsigned long long *dst = buf ? s_alt : s_keys;
+                    dst[tid] = x;
+                    __syncthreads();
+                    y = dst[tid ^ j];
+                    buf ^= 1;
+                } else {
+                    y = __shfl_xor_sync(RN_FULL_MASK, x, j);
+                }
+                const bool keep_max = desc == ((tid & j) == 0);
+                x = keep_max ? (x > y ? x : y) : (x < y ? x : y);
+            }
+        }
+        if (tid < K) sel[(size_t)b * top_k + tid] = x;
+        return;
+    }
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tid; i < P; i += RN_SEL_THREADS) {
@@ -700,11 +761,27 @@ extern "C" size_t rn_nms_workspace_bytes(int n, int top_k) {
     return rn_post_layout(1, n, top_k).total;
 }
 
+// host copy of rn_float_sortable
+static unsigned rn_host_sortable(float f) {
+    unsigned u;
+    memcpy(&u, &f, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// score_range: the scores behind the keys lie in (thresh, 1] (post-processing of probabilities); lets the select kernel bin
+// them in one pass.  Only a hint: keys outside the range are still selected exactly.
 static int rn_launch_select_nms(bool from_boxes, int B, int cap, RnNmsParams &P, const RnGeom &g, const RnDecode &dec,
-                                unsigned char *ws, const RnPostWs &L, cudaStream_t s, const int32_t *seg_off = nullptr) {
+                                unsigned char *ws, const RnPostWs &L, cudaStream_t s, const int32_t *seg_off = nullptr,
+                                const float *score_thresh = nullptr) {
+    unsigned score_lo = 0, score_hi = 0;
+    if (score_thresh && *score_thresh == *score_thresh && *score_thresh < 1.0f) {
+        score_lo = rn_host_sortable(*score_thresh);
+        score_hi = rn_host_sortable(1.0f);
+    }
     rn_launch_pdl(rn_post_select_kernel, dim3(B), dim3(RN_SEL_THREADS), 0, s,
                   reinterpret_cast<const unsigned long long *>(ws + L.keys), reinterpret_cast<const int32_t *>(ws + L.counts), cap,
-                  seg_off, P.top_k, reinterpret_cast<unsigned long long *>(ws + L.sel), reinterpret_cast<int32_t *>(ws + L.nsel));
+                  seg_off, P.top_k, score_lo, score_hi, reinterpret_cast<unsigned long long *>(ws + L.sel),
+                  reinterpret_cast<int32_t *>(ws + L.nsel));
     int rc = rn_check_launch("rn_post_select");
     if (rc) return rc;
     P.sel = reinterpret_cast<unsigned long long *>(ws + L.sel);
@@ -788,7 +865,7 @@ extern "C" int rn_postproc(const float *clas, const float *reg, int B, int A, in
     P.top_k = top_k; P.max_keep = max_keep; P.max_overlap = max_overlap;
     P.out_boxes = reinterpret_cast<float4 *>(boxes); P.out_classes = classes; P.out_scores = scores;
     P.out_idx = anchor_idx; P.out_counts = counts; P.out_ncand = n_candidates;
-    return rn_launch_select_nms(false, B, A, P, g, dec, ws, L, s);
+    return rn_launch_select_nms(false, B, A, P, g, dec, ws, L, s, nullptr, &thresh);
 }
 
 extern "C" int rn_postproc_levels(const float *const *clas_levels, const float *const *reg_levels, int from_logits, int B,
@@ -855,7 +932,7 @@ extern "C" int rn_postproc_levels(const float *const *clas_levels, const float *
     P.top_k = top_k; P.max_keep = max_keep; P.max_overlap = max_overlap;
     P.out_boxes = reinterpret_cast<float4 *>(boxes); P.out_classes = classes; P.out_scores = scores;
     P.out_idx = anchor_idx; P.out_counts = counts; P.out_ncand = n_candidates;
-    return rn_launch_select_nms(false, B, A, P, g, dec, ws, L, s);
+    return rn_launch_select_nms(false, B, A, P, g, dec, ws, L, s, nullptr, &thresh);
 }
 
 extern "C" int rn_nms(const float *boxes, const int64_t *classes, const float *scores, int n, float max_overlap,

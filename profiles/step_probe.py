@@ -1,6 +1,6 @@
 """Times the fused training step (rn_loss_step) on synthetic COCO / Pascal shaped batches; library options can be set from
 the command line (name=value ...).  Used for A/B runs inside one gpurun call and as the ncu target.
-    python profiles/step_probe.py [coco|pascal|b256] [reps] [opt=value ...]"""
+    python profiles/step_probe.py [coco|pascal|b256][:B] [reps] [opt=value ...]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -16,8 +16,10 @@ def main():
     for kv in sys.argv[3:]:
         k, v = kv.split("=")
         _lib.check(lib.rn_set_option(k.encode(), int(v)))
+    which, _, bsz = which.partition(":")   # e.g. pascal:37 = the Pascal shape with 37 images
     cfg = dict(coco=(800, 1344, 80, 20, 16), pascal=(512, 512, 20, 10, 32), b256=(800, 1344, 80, 20, 256))[which]
     H, W, C, M, B = cfg
+    B = int(bsz) if bsz else B
     dev = torch.device("cuda:0")
     anchors = AnchorGenerator()(torch.zeros(1, 3, H, W, device=dev))
     A = anchors.shape[0]
@@ -41,6 +43,6 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     alg = 8 * A * (C + 4) * B
-    print("%s %s: %.4f ms/step  %.1f GB/s  frac %.3f  loss %.6f" % (which, " ".join(sys.argv[3:]), ms, alg / ms / 1e6, alg / ms / 1e6 / 6538.6, caps[0].loss.item()))
+    print("%s B=%d %s: %.4f ms/step  %.1f GB/s  frac %.3f  loss %.6f" % (which, B, " ".join(sys.argv[3:]), ms, alg / ms / 1e6, alg / ms / 1e6 / 6538.6, caps[0].loss.item()))
 
 main()
