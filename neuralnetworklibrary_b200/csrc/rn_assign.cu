@@ -645,27 +645,39 @@ rn_stage_images_kernel(const T *__restrict__ pixels, const int64_t *__restrict__
             const int mis = (int)(reinterpret_cast<uintptr_t>(src) & 3);
             const uint32_t *w0 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(src) - mis);
             const int words = (mis + nb + 3) >> 2;
-            for (int wi = tid; wi < words; wi += 256) {
-                const uint32_t w = __ldg(w0 + wi);
+            for (int wi0 = tid; wi0 < words; wi0 += 4 * 256) {  // four independent word loads per thread in flight
+                uint32_t w4[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int idx = 4 * wi + k - mis;
-                    if (idx >= 0 && idx < nb) {
-                        float v = (float)((w >> (8 * k)) & 0xffu);
-                        if (norm.on) {
-                            const int c = (lo + idx) % C;
-                            v = __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), norm.mean[c]), norm.std[c]);
+                for (int u = 0; u < 4; ++u) w4[u] = (wi0 + u * 256 < words) ? __ldg(w0 + wi0 + u * 256) : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int wi = wi0 + u * 256;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int idx = 4 * wi + k - mis;
+                        if (wi < words && idx >= 0 && idx < nb) {
+                            float v = (float)((w4[u] >> (8 * k)) & 0xffu);
+                            if (norm.on) {
+                                const int c = (lo + idx) % C;
+                                v = __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), norm.mean[c]), norm.std[c]);
+                            }
+                            s_row[lo + idx] = v;
                         }
-                        s_row[lo + idx] = v;
                     }
                 }
             }
         }
     } else {
-        for (int i = tid; i < n; i += 256) {
-            float v = 0.0f;
-            if (row_in && i >= lo && i < hi) v = (float)__ldg(src + (i - lo));
-            s_row[i] = v;
+        for (int i0 = tid; i0 < n; i0 += 8 * 256) {  // eight independent loads per thread in flight
+            float v8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * 256;
+                v8[u] = (row_in && i >= lo && i < hi) ? (float)__ldg(src + (i - lo)) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (i0 + u * 256 < n) s_row[i0 + u * 256] = v8[u];
         }
     }
     __syncthreads();

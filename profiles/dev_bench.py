@@ -42,6 +42,8 @@ for w in what:
         ms, lay, ncand, nkept = bench.time_postproc_levels(COCO, 64, steps, 3, dev, w.endswith("logits"))
         out[w] = {"ms": ms, "layout_ops_ms": lay, "cand": ncand, "kept": nkept,
                   "frac": bench.loss_bytes(64, A, 80, grad=False) / (ms * 1e-3) / 1e9 / peak}
+    elif w == "aux":
+        out[w] = {k: v for k, v in bench.time_aux_kernels(dev, peak).items() if "stage_images" in k or "overlaps" in k}
     elif w == "postproc":
         pms, pwall, ncand, nkept, _ = bench.time_postproc(COCO, 64, steps, 3, dev)
         out[w] = {"ms": pms / steps, "wall_ms": pwall / steps, "frac": bench.loss_bytes(64, A, 80, grad=False) / (pms / steps * 1e-3) / 1e9 / peak}
