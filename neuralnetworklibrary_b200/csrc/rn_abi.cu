@@ -28,7 +28,8 @@ extern "C" int rn_abi_version(void) { return 2; }
 // Process-wide tuning / test switches, set explicitly through the ABI (never read from the environment: a stray
 // variable in a training job must not change which kernel runs).  0 = default behaviour for every option.
 static const char *const g_opt_names[RN_OPT_COUNT] = {"assign_dense", "assign_no_balance", "assign_wbase", "loss_iters",
-                                                      "levels_nchunks", "step_fused", "step_bytemap", "loss_prefetch"};
+                                                      "levels_nchunks", "step_fused", "step_bytemap", "loss_prefetch",
+                                                      "assign_parts"};
 static int g_opt[RN_OPT_COUNT] = {0};
 
 int rn_opt(int id) { return (id >= 0 && id < RN_OPT_COUNT) ? g_opt[id] : 0; }

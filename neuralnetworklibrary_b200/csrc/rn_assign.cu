@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(RN_SPARSE_THREADS)
 rn_assign_sparse_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__restrict__ gt_cats, int M,
                         const __grid_constant__ RnGeom g, float pos_thr, float neg_thr, int32_t *__restrict__ matches,
                         int32_t *__restrict__ npos, uint8_t *__restrict__ m8, int32_t *__restrict__ clean_list,
-                        int32_t *__restrict__ clean_cnt) {
+                        int32_t *__restrict__ clean_cnt, int parts) {
     extern __shared__ __align__(16) unsigned char smem[];
     float4 *s_box = reinterpret_cast<float4 *>(smem);
     float *s_area = reinterpret_cast<float *>(s_box + M);
@@ -349,7 +349,8 @@ rn_assign_sparse_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__re
     __shared__ float s_ub[4][RN_NUM_LEVELS * RN_MAX_K];  // per window: bounding box of its anchors (x1, y1, x2, y2), rounded outwards
     __shared__ unsigned char s_list[128];                // compacted indices of the image's boxes that touch the windows (M <= 128)
     __shared__ int s_nl;
-    const int b = blockIdx.y, row = blockIdx.x;
+    // `parts` CTAs per box may share its candidates (interleaved in steps of 256); see rn_sparse_parts for why it stays 1
+    const int b = blockIdx.y, row = blockIdx.x / parts, part = blockIdx.x - row * parts;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     rn_pdl_trigger();
     const int64_t *cats = gt_cats + (size_t)b * M;
@@ -486,7 +487,7 @@ rn_assign_sparse_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__re
     int cnt = 0;
     if (!BYTES) rn_pdl_wait();  // launched with PDL behind rn_assign_fill_kernel: its background fill must be complete before we write
 #pragma unroll 1
-    for (int idx = tid; idx < total; idx += RN_SPARSE_THREADS) {
+    for (int idx = part * RN_SPARSE_THREADS + tid; idx < total; idx += parts * RN_SPARSE_THREADS) {
         int seg = 0;  // largest seg with s_pref[seg] <= idx (binary search over <= 80 segments)
 #pragma unroll
         for (int step = 64; step > 0; step >>= 1)
@@ -707,6 +708,16 @@ extern "C" int rn_anchors(int H, int W, const double *base, int K, float *anchor
     return rn_check_launch("rn_anchors");
 }
 
+// CTAs per ground-truth box of the sparse kernel (rn_set_option("assign_parts", n)); 1 by default.  Measured (whole step,
+// graph replay): Pascal B=32 63.3 / 63.2 / 64.3 / 66.1 / 69.6 us and COCO B=16 341.4 / 340.6 / 342.2 / 344.6 / 348.1 us for
+// 1 / 2 / 3 / 4 / 8 parts -- the kernel's time is its prologue (dependent loads, box compaction, float64 windows, two
+// barriers), not the candidate loop, and every extra CTA repeats the prologue.
+static int rn_sparse_parts(int M, int B) {
+    (void)M; (void)B;
+    const int p = rn_opt(RN_OPT_ASSIGN_PARTS);
+    return p > 0 ? (p < 16 ? p : 16) : 1;
+}
+
 extern "C" int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, int M, int H, int W,
                          const double *base, int K, const float *anchors, int A, float pos_thr, float neg_thr,
                          int32_t *matches, int32_t *npos, float *max_iou, void *stream) {
@@ -728,9 +739,10 @@ extern "C" int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, i
         if (B <= fill_ctas * 256) {
             rn_assign_fill_kernel<<<fill_ctas, 256, 0, s>>>(matches, n, npos, B);
             const size_t sm = (size_t)M * (sizeof(float4) + sizeof(float));
-            rn_launch_pdl(rn_assign_sparse_kernel<false>, dim3(M, B), dim3(RN_SPARSE_THREADS), sm, s,
+            const int parts = rn_sparse_parts(M, B);
+            rn_launch_pdl(rn_assign_sparse_kernel<false>, dim3(M * parts, B), dim3(RN_SPARSE_THREADS), sm, s,
                           reinterpret_cast<const float4 *>(gt_boxes), gt_cats, M, g, pos_thr, neg_thr, matches, npos,
-                          (uint8_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr);
+                          (uint8_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, parts);
             return rn_check_launch("rn_assign (sparse)");
         }
     }
@@ -773,8 +785,10 @@ extern "C" int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, i
 int rn_assign_bytes(const float *gt_boxes, const int64_t *gt_cats, int B, int M, const RnGeom &g, float pos_thr, float neg_thr,
                     uint8_t *m8, int32_t *npos_acc, int32_t *clean_list, int32_t *clean_cnt, cudaStream_t s) {
     const size_t sm = (size_t)M * (sizeof(float4) + sizeof(float));
-    rn_assign_sparse_kernel<true><<<dim3(M, B), RN_SPARSE_THREADS, sm, s>>>(
-        reinterpret_cast<const float4 *>(gt_boxes), gt_cats, M, g, pos_thr, neg_thr, nullptr, npos_acc, m8, clean_list, clean_cnt);
+    const int parts = rn_sparse_parts(M, B);
+    rn_assign_sparse_kernel<true><<<dim3(M * parts, B), RN_SPARSE_THREADS, sm, s>>>(
+        reinterpret_cast<const float4 *>(gt_boxes), gt_cats, M, g, pos_thr, neg_thr, nullptr, npos_acc, m8, clean_list, clean_cnt,
+        parts);
     return rn_check_launch("rn_assign (byte map)");
 }
 

@@ -44,6 +44,7 @@ enum RnOption {
     RN_OPT_STEP_FUSED,         // != 0: rn_loss_step runs as ONE persistent kernel (rn_step.cu) where its conditions hold
     RN_OPT_STEP_BYTEMAP,       // != 0: rn_loss_step takes its three-kernel byte-map chain instead of rn_assign + rn_loss
     RN_OPT_LOSS_PREFETCH,      // L2 prefetch of rn_loss_kernel before its PDL wait: 1 first sub-tile, 2 all (default), 3 + next wave
+    RN_OPT_ASSIGN_PARTS,       // > 0: CTAs per ground-truth box of the sparse assignment kernel (default: by M * B, 1..4)
     RN_OPT_COUNT
 };
 int rn_opt(int id);
