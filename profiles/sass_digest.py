@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "neuralnetworklibrary_b200", "libretina_sm100.so")
 WATCH = ["FFMA2", "FMUL2", "FADD2", "FFMA", "MUFU", "LDG.E.128", "LDG.E.NA.128", "STG.E.EF.128", "STG.E.128", "LDG.E.U8", "LDG.E.S8",
-         "UBLKCP", "SYNCS", "HMMA", "UTCHMMA", "UTCMMA", "LDTM", "ATOM", "RED", "BAR.SYNC", "CCTL.IVALL", "LDL", "STL", "DADD", "DMUL",
+         "UBLKCP", "SYNCS", "HMMA", "UTCHMMA", "UTCMMA", "LDTM", "ATOM", "RED", "BAR.SYNC", "CCTL.IVALL", "CCTL.E.PF2", "LDL", "STL", "DADD", "DMUL",
          "ACQBULK", "LDG.E.STRONG", "NANOSLEEP"]
 
 
