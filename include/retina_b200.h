@@ -199,6 +199,13 @@ int rn_loss_levels(const float *const *clas_levels /*host[5]*/, const float *con
 size_t rn_peer_exchange_bytes(int world);
 int rn_peer_exchange(float *out3, void *const *peer_bufs /*host [world]*/, int rank, int world, uint32_t *seq, void *stream);
 
+/* The same with separate input and output: total3 receives the sums, in3 (this rank's share) is left untouched -- repeating
+ * the call for the same step is then harmless.  Used by the pipelined form of the captured step (SSD_loss.capture(...,
+ * pipelined_exchange=True)): the exchange of step k runs on a parallel branch at the START of step k+1's CUDA graph, beside the
+ * assignment and streaming kernels, so nothing on the step's critical path waits for NVLink or for a peer. */
+int rn_peer_exchange_to(const float *in3, float *total3, void *const *peer_bufs /*host [world]*/, int rank, int world,
+                        uint32_t *seq, void *stream);
+
 /* Backward with a non-unit upstream gradient: scales dclas[n_clas], dreg[n_reg] in place by the
  * DEVICE scalar *grad_out; the kernel exits immediately when *grad_out == 1 (what loss.backward()
  * passes, General/Learner.py:514), so the common case costs one empty launch and no host sync. */

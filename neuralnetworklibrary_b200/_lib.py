@@ -122,6 +122,7 @@ PROTOTYPES = {
                                _f32p, _f32p, _f32p, _f32p, _i32p, _i32p, _vp, C.c_size_t, _vp, C.c_size_t, _vp]),
     "rn_peer_exchange_bytes": (C.c_size_t, [C.c_int]),
     "rn_peer_exchange": (C.c_int, [_f32p, _pp, C.c_int, C.c_int, _vp, _vp]),
+    "rn_peer_exchange_to": (C.c_int, [_f32p, _f32p, _pp, C.c_int, C.c_int, _vp, _vp]),
     "rn_scale_grads": (C.c_int, [_f32p, C.c_size_t, _f32p, C.c_size_t, _f32p, _vp]),
     "rn_postproc_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "rn_postproc": (C.c_int, [_f32p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f64p, C.c_int, _f32p,

@@ -319,11 +319,11 @@ struct RnPeers {
 };
 
 __global__ void __launch_bounds__(32)
-rn_peer_exchange_kernel(float *__restrict__ out3, const RnPeers peers, int rank, int world, uint32_t *__restrict__ seq) {
+rn_peer_exchange_kernel(const float *in3, float *out3, const RnPeers peers, int rank, int world, uint32_t *__restrict__ seq) {
     const int t = threadIdx.x;
     const uint32_t e = *seq + 1u;
     const int set = (int)(e & 1u);
-    const float v0 = out3[0], v1 = out3[1], v2 = out3[2];
+    const float v0 = in3[0], v1 = in3[1], v2 = in3[2];  // in3 may equal out3 (rn_peer_exchange)
     bool timed_out = false;
     if (t < world) {
         float *slot = peers.buf[t] + ((size_t)set * world + rank) * 4;
@@ -377,18 +377,23 @@ extern "C" size_t rn_peer_exchange_bytes(int world) {
     return (size_t)2 * world * 4 * sizeof(float) + (size_t)2 * world * sizeof(uint32_t);
 }
 
-extern "C" int rn_peer_exchange(float *out3, void *const *peer_bufs, int rank, int world, uint32_t *seq, void *stream) {
+extern "C" int rn_peer_exchange_to(const float *in3, float *out3, void *const *peer_bufs, int rank, int world, uint32_t *seq,
+                                   void *stream) {
     if (world < 1 || world > RN_PEER_MAX || rank < 0 || rank >= world)
         return rn_set_error(RN_ERR_INVALID_ARG, "rn_peer_exchange: rank=%d world=%d (at most %d ranks)", rank, world, RN_PEER_MAX);
-    if (!out3 || !peer_bufs || !seq) return rn_set_error(RN_ERR_INVALID_ARG, "rn_peer_exchange: null pointer");
+    if (!in3 || !out3 || !peer_bufs || !seq) return rn_set_error(RN_ERR_INVALID_ARG, "rn_peer_exchange: null pointer");
     RnPeers P;
     memset(&P, 0, sizeof(P));
     for (int r = 0; r < world; ++r) {
         if (!peer_bufs[r] || (((uintptr_t)peer_bufs[r]) & 15)) return rn_set_error(RN_ERR_INVALID_ARG, "rn_peer_exchange: bad buffer of rank %d", r);
         P.buf[r] = reinterpret_cast<float *>(peer_bufs[r]);
     }
-    rn_peer_exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(out3, P, rank, world, seq);
+    rn_peer_exchange_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(in3, out3, P, rank, world, seq);
     return rn_check_launch("rn_peer_exchange");
+}
+
+extern "C" int rn_peer_exchange(float *out3, void *const *peer_bufs, int rank, int world, uint32_t *seq, void *stream) {
+    return rn_peer_exchange_to(out3, out3, peer_bufs, rank, world, seq, stream);
 }
 
 extern "C" int rn_scale_grads(float *dclas, size_t n_clas, float *dreg, size_t n_reg, const float *grad_out,

@@ -270,17 +270,39 @@ class CapturedLossStep(object):
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         exchange = cfg.get("exchange")
+        self.pipelined = bool(cfg.get("exchange_pipelined")) and exchange is not None
+        self.exchange = exchange
         with torch.cuda.stream(side):   # warm-up outside capture (lazy module load); every rank runs the same sequence
             _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, True, self.bufs)
             if exchange is not None:
                 exchange(self.bufs["out3"])
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, True, self.bufs)
-            if exchange is not None:
-                exchange(self.bufs["out3"])
+        if self.pipelined:
+            # Two graphs that differ only in the buffer of the three scalars.  Graph p computes step k into share[p] and, on a
+            # parallel branch that starts with the graph, sums the PREVIOUS step over the ranks (share[1-p] -> totals[1-p],
+            # rn_peer_exchange_to): the NVLink round trip and the wait for the peers run beside the assignment and streaming
+            # kernels instead of behind the final reduction, where they cost 5-10 us per step.
+            self._share = [self.bufs["out3"], torch.zeros_like(self.bufs["out3"])]
+            self._totals = [torch.zeros_like(self.bufs["out3"]) for _ in range(2)]
+            self._graphs, self._parity = [], 1
+            for p in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    main = torch.cuda.current_stream(dev)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        exchange.exchange_to(self._share[1 - p], self._totals[1 - p])
+                    _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, True, dict(self.bufs, out3=self._share[p]))
+                    main.wait_stream(side)
+                self._graphs.append(g)
+            self.graph = self._graphs[0]
+        else:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                _launch_loss(anchors, reg, clas, gt_boxes, gt_cats, cfg, True, self.bufs)
+                if exchange is not None:
+                    exchange(self.bufs["out3"])
         self.exchange_in_graph = exchange is not None
         self.out3 = self.bufs["out3"]
         self.loss, self.reg_loss, self.clas_loss = self.out3.unbind(0)
@@ -308,8 +330,29 @@ class CapturedLossStep(object):
         return assign_batch(anchors, gt_boxes, gt_cats, self.cfg["pos_thresh"], self.cfg["neg_thresh"])[0]
 
     def replay(self):
+        if self.pipelined:
+            self._parity ^= 1
+            self._graphs[self._parity].replay()
+            self.out3 = self._share[self._parity]   # this rank's share of the newest step
+            self.loss, self.reg_loss, self.clas_loss = self.out3.unbind(0)
+            return self.loss
         self.graph.replay()
         return self.loss
+
+    def total(self):
+        """[loss, reg_loss, clas_loss] of the newest replay summed over the ranks (device tensor).  Pipelined exchange: one
+        rn_peer_exchange_to launch now (a collective: every rank calls it at the same point); otherwise the step's own out3,
+        which already holds the sums (exchange inside the graph) or this rank's share (no exchange configured)."""
+        if not self.pipelined:
+            return self.out3
+        p = self._parity
+        return self.exchange.exchange_to(self._share[p], self._totals[p])
+
+    @property
+    def previous_total(self):
+        """Pipelined exchange: the sums of the replay BEFORE the newest one, which the newest replay computed on its parallel
+        branch (device tensor [3]; None without the pipelined exchange)."""
+        return self._totals[1 - self._parity] if self.pipelined else None
 
 
 class CapturedLevelLossStep(object):
@@ -405,6 +448,13 @@ class PeerExchange(object):
                                                 _lib.stream_ptr(out3.device)))
         return out3
 
+    def exchange_to(self, in3, total3):
+        """total3 <- sum over the ranks of in3 (rn_peer_exchange_to); in3 keeps this rank's share, so exchanging the same
+        step twice is harmless."""
+        _lib.check(_lib.load().rn_peer_exchange_to(_lib.ptr(in3), _lib.ptr(total3), self.ptrs, self.rank, self.world,
+                                                   _lib.ptr(self.seq), _lib.stream_ptr(in3.device)))
+        return total3
+
 
 class SSD_loss(object):
     """SSD / RetinaNet loss: (1-beta) * smooth-L1 + beta * focal (reference Vision.py:1607-1644).
@@ -493,11 +543,14 @@ class SSD_loss(object):
         self.reg_loss, self.clas_loss = reg_loss, clas_loss   # Vision.py:1643
         return loss
 
-    def capture(self, activ, target):
+    def capture(self, activ, target, pipelined_exchange=False):
         """Captures forward+backward for the given static tensors into a CUDA graph.  Returns a CapturedLossStep.  With
         distributed=True and peer_exchange the sum of the loss scalars over the ranks (rn_peer_exchange) is part of the graph
         and .loss / .reg_loss / .clas_loss hold the global values; with the NCCL exchange the graph holds this rank's share
-        and the caller reduces it (reduce_loss_scalars)."""
+        and the caller reduces it (reduce_loss_scalars).  pipelined_exchange=True (with peer_exchange): the graph ends with
+        the exchange of a step's scalars runs at the START of the next replay, on a parallel branch of its graph beside the
+        assignment and streaming kernels -- .loss etc. stay this rank's share, .previous_total holds the sums of the step
+        before the newest one and .total() sums the newest step over the ranks on demand (a collective)."""
         anchors, reg, clas = activ[0], activ[1], activ[2]
         BBoxes, Cats = target[0], target[1]
         _lib.require_cuda(BBoxes, "BBoxes", torch.float32)
@@ -515,7 +568,8 @@ class SSD_loss(object):
                 raise ValueError("capture() needs contiguous static tensors")
         cfg = dict(alpha=self.alpha, gamma=self.gamma, beta=self.beta, pos_thresh=self.pos_thresh,
                    neg_thresh=self.neg_thresh, world_size=1, group=None, global_batch=self.global_batch,
-                   from_logits=self.from_logits, keep_matches=self.keep_matches, exchange=self._exchange())
+                   from_logits=self.from_logits, keep_matches=self.keep_matches, exchange=self._exchange(),
+                   exchange_pipelined=bool(pipelined_exchange))
         return CapturedLossStep(cfg, anchors, reg.detach(), clas.detach(), BBoxes, Cats)
 
     @property

@@ -76,7 +76,29 @@ def main():
         torch.cuda.synchronize()
         assert cap.exchange_in_graph and cap.loss.item() == ls.item(), (cap.loss.item(), ls.item())
         assert torch.equal(cap.dclas, cs.grad)
-        peer_ok = "ok (%d kernels per replay)" % cap.kernels_per_replay
+        # pipelined form: the exchange of a step runs on a parallel branch at the start of the NEXT replay's graph
+        # (rn_peer_exchange_to); the static regression input changes between replays, so a stale or mixed-up sum would show.
+        # Everything is bit-identical to the all-gather path and the gradients are untouched.
+        t0, t1 = target[0].contiguous(), target[1].contiguous()
+        rs3, cs3 = (activ[1] * 0.5).requires_grad_(True), activ[2].clone().requires_grad_(True)
+        lb = shard([anchors, rs3, cs3], target)
+        want = {"A": ls.item(), "B": lb.item()}
+        assert want["A"] != want["B"]
+        reg_in = activ[1].contiguous().clone()
+        capp = peer.capture([anchors, reg_in, activ[2].contiguous()], [t0, t1], pipelined_exchange=True)
+        assert capp.pipelined
+        prev = None
+        for name in "ABBABA":
+            reg_in.copy_(activ[1] if name == "A" else activ[1] * 0.5)
+            capp.replay()
+            tot = capp.total().clone()
+            torch.cuda.synchronize()
+            assert tot[0].item() == want[name], (name, tot[0].item(), want[name])
+            if prev is not None:
+                assert capp.previous_total[0].item() == want[prev], (name, prev, capp.previous_total[0].item())
+            prev = name
+        assert torch.equal(capp.dclas, cs.grad)
+        peer_ok = "ok (%d kernels per replay; pipelined exchange ok)" % cap.kernels_per_replay
 
     # detections: shard + gather == full batch
     ci, ri = syn.make_infer_activations(B, an.shape[0], C, seed=78, anchors=an, mu=-5.0, clusters=5)
