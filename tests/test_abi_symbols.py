@@ -73,6 +73,12 @@ def test_argument_validation_returns_error_codes_without_a_device():
     assert lib.rn_loss_step(None, None, None, None, 2, 100, 20, 4, 64, 64, None, 9, None, 0.5, 0.4, 0.25, 2.0, 0.5, 2, 0,
                             None, None, None, None, None, None, None, 0, None, 0, None) == INVALID
     assert lib.rn_loss_step_state_init(None, 0, None) == WORKSPACE
+    # the multi-GPU exchange: world / rank out of range, null pointers, more ranks than the kernel's 16 slots
+    assert lib.rn_peer_exchange_bytes(0) == 0 and lib.rn_peer_exchange_bytes(8) >= 8 * 2 * 16
+    assert lib.rn_peer_exchange(None, None, 0, 0, None, None) == INVALID
+    assert lib.rn_peer_exchange(None, None, 0, 2, None, None) == INVALID
+    assert lib.rn_peer_exchange_to(None, None, None, 3, 2, None, None) == INVALID and b"rn_peer_exchange" in lib.rn_last_error()
+    assert lib.rn_peer_exchange_to(None, None, None, 0, 17, None, None) == INVALID
     # top_k outside the supported range, workspace too small
     import numpy as np
     f4 = (ctypes.c_float * 4)(0, 0, 0, 0)
