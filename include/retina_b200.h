@@ -61,6 +61,8 @@ int rn_abi_version(void);
  *   "step_bytemap" (!= 0: rn_loss_step takes its three-kernel byte-map chain instead of rn_assign + rn_loss),
  *   "loss_prefetch" (L2 prefetch of rn_loss before its dependency wait: 1 first sub-tile / no look-ahead in rn_loss_levels,
  *   2 all of the CTA's, 3 + next wave), "assign_parts" (> 0: CTAs per ground-truth box of the sparse assignment kernel).
+ * "step_fused" / "step_bytemap" can only be switched on in a library built with -DRN_EXPERIMENTAL (both measured slower than
+ * the default and are left out of the default build); rn_get_option("experimental") tells (1 / 0, read-only).
  * rn_set_option returns RN_ERR_INVALID_ARG for an unknown name; rn_get_option returns -1 for one. */
 int rn_set_option(const char *name, int value);
 int rn_get_option(const char *name);

@@ -16,7 +16,12 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 # RETINA_B200_LIB overrides the library path (A/B comparisons of builds); the default is the in-tree build.
 LIB_PATH = os.environ.get("RETINA_B200_LIB") or os.path.join(_PKG, "libretina_sm100.so")
-SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_step.cu", "rn_post.cu", "rn_loss_levels.cu", "rn_metrics.cu"]
+SOURCES = ["rn_abi.cu", "rn_assign.cu", "rn_loss.cu", "rn_loss_inst_logits.cu", "rn_step.cu", "rn_post.cu", "rn_loss_levels.cu",
+           "rn_metrics.cu"]
+# RN_EXTRA_NVCC_FLAGS=-DRN_EXPERIMENTAL (with a forced rebuild) adds the two alternative implementations of rn_loss_step that
+# measured slower than the default (the persistent kernel and the byte-map chain): 22 more kernels
+if "-DRN_EXPERIMENTAL" in os.environ.get("RN_EXTRA_NVCC_FLAGS", ""):
+    SOURCES += ["rn_loss_inst_bytes.cu", "rn_loss_inst_bytes_logits.cu"]
 BUILD_DIR = os.path.join(_PKG, "csrc", "_build")   # object files (git-ignored); the .so is what travels
 
 NVCC_FLAGS = [
@@ -176,6 +181,11 @@ def check(rc):
         if rc == RN_ERR_INVALID_ARG:
             raise ValueError(msg)  # the reference reports bad arguments as ValueError (Learner.py:339-340)
         raise RetinaB200Error("libretina_sm100 error %d: %s" % (rc, msg))
+
+
+def has_experimental():
+    """True when the loaded library was built with -DRN_EXPERIMENTAL (the opt-in implementations of rn_loss_step)."""
+    return load().rn_get_option(b"experimental") == 1
 
 
 class option(object):

@@ -41,14 +41,25 @@ static int rn_opt_index(const char *name) {
     return -1;
 }
 
+// The two alternative implementations of rn_loss_step (one persistent kernel; the byte-map chain) measured slower than the
+// default and are only compiled with -DRN_EXPERIMENTAL (RN_EXTRA_NVCC_FLAGS at build time): 22 of the library's kernels.
+#ifdef RN_EXPERIMENTAL
+static const int g_experimental = 1;
+#else
+static const int g_experimental = 0;
+#endif
+
 extern "C" int rn_set_option(const char *name, int value) {
     const int i = rn_opt_index(name);
     if (i < 0) return rn_set_error(RN_ERR_INVALID_ARG, "rn_set_option: unknown option '%s'", name ? name : "(null)");
+    if (!g_experimental && value != 0 && (i == RN_OPT_STEP_FUSED || i == RN_OPT_STEP_BYTEMAP))
+        return rn_set_error(RN_ERR_INVALID_ARG, "rn_set_option: '%s' needs a library built with -DRN_EXPERIMENTAL", name);
     g_opt[i] = value;
     return RN_OK;
 }
 
 extern "C" int rn_get_option(const char *name) {
+    if (name && strcmp(name, "experimental") == 0) return g_experimental;  // read-only: how the library was built
     const int i = rn_opt_index(name);
     return i < 0 ? -1 : g_opt[i];
 }

@@ -781,6 +781,7 @@ extern "C" int rn_assign(const float *gt_boxes, const int64_t *gt_cats, int B, i
     return rn_check_launch("rn_assign");
 }
 
+#ifdef RN_EXPERIMENTAL
 // The byte-map assignment of rn_loss_step (declared in rn_common.cuh): one launch, no fill.
 int rn_assign_bytes(const float *gt_boxes, const int64_t *gt_cats, int B, int M, const RnGeom &g, float pos_thr, float neg_thr,
                     uint8_t *m8, int32_t *npos_acc, int32_t *clean_list, int32_t *clean_cnt, cudaStream_t s) {
@@ -791,6 +792,7 @@ int rn_assign_bytes(const float *gt_boxes, const int64_t *gt_cats, int B, int M,
         parts);
     return rn_check_launch("rn_assign (byte map)");
 }
+#endif
 
 extern "C" int rn_max_overlaps(const float *gt_boxes, const int64_t *gt_cats, int B, int M, int H, int W,
                                const double *base, int K, const float *anchors, int A, float *out, void *stream) {

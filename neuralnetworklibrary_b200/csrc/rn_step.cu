@@ -98,6 +98,7 @@ struct RnStepParams {
 #endif
 };
 
+#ifdef RN_EXPERIMENTAL  // the persistent kernel (device code below) and the byte-map chain: opt-in at build time
 __device__ __forceinline__ int rn_ld_acquire(const int *p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -621,11 +622,14 @@ rn_step_kernel(const __grid_constant__ RnStepParams S, const __grid_constant__ R
     stamp(3);
 }
 
+#endif  // RN_EXPERIMENTAL
+
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
 static inline size_t rn_up256(size_t x) { return (x + 255) / 256 * 256; }
 
+#ifdef RN_EXPERIMENTAL
 // Chunk grid for `grid` persistent CTAs: k sub-tiles per chunk, k in 2..6 chosen so that the number of chunks is just under
 // a whole number of rounds of the grid (ties: the larger chunk); rows per chunk aligned so that every chunk of clas starts on
 // a 128-byte boundary.  Pure function of (B*A, C, grid).
@@ -654,6 +658,8 @@ static RnStepPlan rn_step_plan(long long total_rows, int A, int C, int grid) {
     best.slots = (best.chunk_rows + A - 1) / A + 1;
     return best;
 }
+
+#endif
 
 // Two caller-owned buffers.  `state` (ctrl | done | npos_acc | byte map) must be all-zero when a call starts and is all-zero
 // again when it ends -- whatever the shapes, so one grow-only zero-initialised buffer serves calls of any shape.  `workspace`
@@ -715,6 +721,7 @@ extern "C" int rn_loss_step_state_init(void *state, size_t state_bytes, void *st
     return RN_OK;
 }
 
+#ifdef RN_EXPERIMENTAL
 #ifdef RN_STEP_TIMING
 static unsigned long long *g_step_dbg = nullptr;
 extern "C" void rn_step_debug_buffer(void *p) { g_step_dbg = reinterpret_cast<unsigned long long *>(p); }
@@ -764,6 +771,8 @@ static int rn_step_dispatch(bool g2, bool grad, RnStepParams &S, const RnGeom &g
     }
 }
 
+#endif  // RN_EXPERIMENTAL
+
 extern "C" int rn_loss_step(const float *clas, const float *reg, const float *gt_boxes, const int64_t *gt_cats, int B, int A,
                             int C, int M, int H, int W, const double *base, int K, const float *anchors, float pos_thr,
                             float neg_thr, double alpha, double gamma, double beta, int B_global, int from_logits,
@@ -787,9 +796,12 @@ extern "C" int rn_loss_step(const float *clas, const float *reg, const float *gt
     if (!state || state_bytes < Z.total || (((uintptr_t)state) & 255))
         return rn_set_error(RN_ERR_WORKSPACE, "rn_loss_step: state needs %zu bytes, 256-byte aligned and zero-initialised", Z.total);
     unsigned char *ws = reinterpret_cast<unsigned char *>(workspace);
+#ifdef RN_EXPERIMENTAL
     unsigned char *zs = reinterpret_cast<unsigned char *>(state);
     cudaStream_t s = (cudaStream_t)stream;
+#endif
 
+#ifdef RN_EXPERIMENTAL
     const bool fused = !anchors && M >= 1 && M <= RN_STEP_MAXM && neg_thr >= 0.2f && pos_thr >= neg_thr &&
                        (long long)B * A <= 0x7fffffffLL - 65536 && rn_opt(RN_OPT_STEP_FUSED) != 0;
     const bool bytemap = !fused && !anchors && M >= 1 && M < RN_STEP_MAXM && neg_thr >= 0.2f && pos_thr >= neg_thr &&
@@ -817,6 +829,9 @@ extern "C" int rn_loss_step(const float *clas, const float *reg, const float *gt
                             by.npos_acc, &by, B, A, C, M, H, W, base, K, nullptr, alpha, gamma, beta, B_global, dclas, dreg, out3,
                             ws + L.loss_ws, rn_loss_workspace_bytes(B, A, C), stream);
     }
+#else
+    const bool fused = false;
+#endif
     if (!fused) {  // the separate kernels: rn_assign (dense or sparse) + rn_loss
         int32_t *m32 = matches_out ? matches_out : reinterpret_cast<int32_t *>(ws + L.matches32);
         int32_t *n32 = npos_out ? npos_out : reinterpret_cast<int32_t *>(ws + L.npos32);
@@ -830,6 +845,7 @@ extern "C" int rn_loss_step(const float *clas, const float *reg, const float *gt
                        dclas, dreg, out3, ws + L.loss_ws, lw, stream);
     }
 
+#ifdef RN_EXPERIMENTAL
     const int V = (C % 4 == 0) ? 4 : 1;
     if ((long long)A * (C / V) > 0x7fffffffLL - RN_LOSS_TILE) return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: A*C too large");
     if (V == 4 && ((((uintptr_t)clas) | ((uintptr_t)dclas) | ((uintptr_t)probs_out)) & 15))
@@ -879,4 +895,7 @@ extern "C" int rn_loss_step(const float *clas, const float *reg, const float *gt
     if (V == 4 && C == 20) return rn_step_dispatch<4, 5, false>(g2, grad, S, g, s);
     if (V == 4) return rn_step_dispatch<4, 0, false>(g2, grad, S, g, s);
     return rn_step_dispatch<1, 0, false>(g2, grad, S, g, s);
+#else
+    return rn_set_error(RN_ERR_INVALID_ARG, "rn_loss_step: unreachable");
+#endif
 }

@@ -32,6 +32,12 @@ def test_host_only_entry_points():
     assert lib.rn_get_option(b"assign_dense") == 0 and lib.rn_get_option(b"no_such_option") == -1
     assert lib.rn_set_option(b"no_such_option", 1) == _lib.RN_ERR_INVALID_ARG
     assert lib.rn_set_option(b"loss_iters", 2) == 0 and lib.rn_get_option(b"loss_iters") == 2 and lib.rn_set_option(b"loss_iters", 0) == 0
+    # the opt-in step variants exist only in builds with -DRN_EXPERIMENTAL; a default build refuses to select them
+    assert lib.rn_get_option(b"experimental") in (0, 1)
+    if lib.rn_get_option(b"experimental") == 0:
+        assert lib.rn_set_option(b"step_fused", 1) == _lib.RN_ERR_INVALID_ARG and b"RN_EXPERIMENTAL" in lib.rn_last_error()
+        assert lib.rn_set_option(b"step_bytemap", 1) == _lib.RN_ERR_INVALID_ARG and lib.rn_set_option(b"step_fused", 0) == 0
+        assert lib.rn_get_option(b"step_fused") == 0
     assert lib.rn_loss_step_workspace_bytes(16, 201600, 80) % 256 == 0 and lib.rn_loss_step_state_bytes(16, 201600) >= 16 * 201600
     assert lib.rn_num_anchors(512, 512, 9) == 49104
     assert lib.rn_num_anchors(800, 1333, 9) == 200700
