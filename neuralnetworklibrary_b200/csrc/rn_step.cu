@@ -1,17 +1,19 @@
-// rn_step.cu -- the whole training step of the path (anchor/GT assignment + focal/smooth-L1 loss forward AND backward +
-// the final reduction) in ONE persistent kernel launch.
+// rn_step.cu -- rn_loss_step, the training step of the path as one library call (anchor/GT assignment + focal/smooth-L1 loss
+// forward AND backward + the final reduction): by default the kernels of rn_assign + rn_loss chained with programmatic
+// dependent launch; with -DRN_EXPERIMENTAL also as ONE persistent kernel launch (the rest of this comment) or as a three-kernel
+// byte-map chain.
 //
 // Replaces (reference file:line): match_anchors_objects Vision.py:1474-1511 (+ jaccard :234-256, the padding strip
 // :1637-1638), ssd1 :1568-1605, focal_loss_retina :1513-1530, smoothL1_loss_retina :1532-1566, SSD_loss.__call__
 // :1620-1644 and the autograd replay of all of it (General/Learner.py:514).
 //
-// Status: OPT-IN (rn_set_option("step_fused", 1)); rn_loss_step launches the separate kernels by default, because they are
-// still faster.  Measured on B200 (profiles/r02_summary.md; CUDA-graph replay, 2 rotating input sets):
+// Status of the persistent kernel: OPT-IN at build time (-DRN_EXPERIMENTAL) and at run time (rn_set_option("step_fused", 1));
+// rn_loss_step launches the separate kernels by default, because they are still faster.  Measured on B200 (profiles/r02_summary.md; CUDA-graph replay, 2 rotating input sets):
 //                                     separate kernels        this kernel
 //     COCO  B=16  (2.17 GB)           0.352 ms  (0.94)        0.394 ms  (0.84)
 //     Pascal B=32 (302 MB)            0.063 ms  (0.73)        0.082 ms  (0.56)
 //     COCO  B=256 (34.7 GB)           5.36  ms  (0.99)        6.03  ms  (0.88)
-// The per-CTA %globaltimer stamps (build with -DRN_STEP_TIMING, profiles/step_timing.py) show where it goes for COCO B=16:
+// The per-CTA %globaltimer stamps (build with -DRN_EXPERIMENTAL -DRN_STEP_TIMING, profiles/step_timing.py) show where it goes for COCO B=16:
 // phase A 8 us (median; 16 us for the last CTA), phase B 363 us with a 34 us spread between the first and the last CTA to run
 // out of tickets, phase C 9 us.  So the three latency-bound pieces the single launch was meant to remove come back as phases
 // of similar length, and the streaming phase is no faster than rn_loss_kernel's 340 us.

@@ -1,5 +1,5 @@
-"""Per-CTA %globaltimer stamps of rn_step_kernel.  Needs a library built with -DRN_STEP_TIMING:
-    RN_EXTRA_NVCC_FLAGS=-DRN_STEP_TIMING python -c "from neuralnetworklibrary_b200 import _lib; _lib.build_library(force=True)" """
+"""Per-CTA %globaltimer stamps of rn_step_kernel.  Needs a library built with the opt-in step variants and -DRN_STEP_TIMING:
+    RN_EXTRA_NVCC_FLAGS="-DRN_EXPERIMENTAL -DRN_STEP_TIMING" python -c "from neuralnetworklibrary_b200 import _lib; _lib.build_library(force=True)" """
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
