@@ -354,7 +354,17 @@ rn_assign_sparse_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__re
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     rn_pdl_trigger();
     const int64_t *cats = gt_cats + (size_t)b * M;
-    if (cats[row] < 0) {  // padding row (Vision.py:1637-1638); uniform over the CTA
+    // every global load the prologue needs is issued before the first one is consumed (one L2 round trip instead of three):
+    // this CTA's box, its category, and -- warp 0 -- the first 32 slots of the image for the compaction below
+    const float4 me = gt_boxes[(size_t)b * M + row];
+    const int64_t my_cat = cats[row];
+    int64_t cat0 = -1;
+    float4 box0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == 0 && lane < M) {
+        cat0 = cats[lane];
+        box0 = gt_boxes[(size_t)b * M + lane];
+    }
+    if (my_cat < 0) {  // padding row (Vision.py:1637-1638); uniform over the CTA
         // Every CTA of a PDL-launched grid must wait: the grid's completion is what the loss kernel behind it waits for,
         // and it only implies the completion of rn_assign_fill_kernel if no CTA retires without having waited for it.
         if (!BYTES) rn_pdl_wait();
@@ -365,11 +375,11 @@ rn_assign_sparse_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__re
         int cnt = 0, self = 0;
         for (int j0 = 0; j0 < M; j0 += 32) {
             const int j = j0 + lane;
-            const bool valid = (j < M) && cats[j] >= 0;
+            const bool valid = (j < M) && (j0 == 0 ? cat0 : cats[j]) >= 0;
             const unsigned mask = __ballot_sync(RN_FULL_MASK, valid);
             const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
             if (valid) {
-                const float4 bx = boxes[j];
+                const float4 bx = j0 == 0 ? box0 : boxes[j];
                 s_box[pos] = bx;
                 s_area[pos] = rn_area(bx);
                 if (j == row) self = pos;
@@ -383,7 +393,6 @@ rn_assign_sparse_kernel(const float4 *__restrict__ gt_boxes, const int64_t *__re
         }
     }
     // ---- candidate windows: one per (level, base box), computed by warps 1.. while warp 0 compacts ----
-    const float4 me = gt_boxes[(size_t)b * M + row];
     const double wg = (double)me.z - (double)me.x, hg = (double)me.w - (double)me.y;
     const int K = g.K, nseg = RN_NUM_LEVELS * K;
     for (int sg = tid - 32; sg >= 0 && sg < nseg; sg += RN_SPARSE_THREADS - 32) {
