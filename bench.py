@@ -2,21 +2,26 @@
 """Benchmark of the RetinaNet loss / post-processing hot path (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (torchrun launches N ranks)
-    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port, host cores)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the UNMODIFIED reference (oracle/_ref) on the host cores
 
 A "step" is one pass of the hot path over one synthetic COCO-shaped batch per GPU: anchor assignment +
 focal / smooth-L1 loss forward AND backward (SSD_loss(...) then loss.backward()), B=16 images of
 800x1344 (A = 201 600 anchors, 80 classes, M = 20 ground-truth slots) per GPU -- BASELINE.json
 configs[2].  Scaling is weak (per-GPU batch fixed); images shard over ranks with one 12-byte exchange of
-the loss scalars per step.  One JSON line is printed by rank 0.
+the loss scalars per step (--exchange: by default a kernel over peer-mapped memory that runs beside the NEXT
+step's kernels, see time_loss_graph).  One JSON line is printed by rank 0.
 
-  value     images/s, inputs resident in HBM, through the public drop-in API (SSD_loss + backward)
+  value     images/s, inputs resident in HBM: CUDA-graph replays of the step captured from the public drop-in API
+            (SSD_loss.capture); `eager` is the same step call by call (SSD_loss(...) + loss.backward())
   e2e       same API, but every step first copies that step's inputs from pinned host memory and ends
             with a device->host read of the loss
   roofline  the streaming loss kernel: algorithmic bytes 8*A*(C+4) per image / CUDA-event time of the
             rn_loss call measured inside the timed region, against MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (a port of the reference's algorithm) on this box's host cores
-Extra keys `postproc` and `pascal` report BASELINE.json configs[3] / configs[1] the same way.
+  cpu_baseline  the unmodified reference on this box's host cores (kind "reference"; the C port of its algorithm as
+            cpu_baseline_port), reference_cuda the reference on the B200 itself
+Extra keys `postproc`, `pascal`, `coco_b256_sharded` report BASELINE.json configs[3] / configs[1] / configs[4] the same
+way; `logits`, `levels`, `levels_logits`, `postproc_levels*` the variants that read the heads' logits / NCHW level tensors;
+`aux_kernels` the kernels around the two hot paths; `parity` ties the first timed batch to the CPU oracle.
 """
 import argparse
 import json
