@@ -82,8 +82,15 @@ __device__ __forceinline__ int rn_key_anchor(unsigned long long key, bool pack) 
 // All R*NV loads of a step are issued before the first compare, so every warp keeps R*NV independent
 // 128-bit requests in flight (the first version had a runtime-trip-count loop: one request in flight
 // per warp and 27 % of DRAM peak, profiles/r01_first_pass.md).
+// Resident CTAs per SM the scan kernel is compiled for.  The number matters less than its presence: with a bare
+// __launch_bounds__(256) ptxas settled on 34 registers and spread the 10 independent 128-bit loads of a step over 100
+// instructions (2-4 in flight); told the register budget (5 CTAs: 47 registers) it issues them back to back.
+// COCO B=64 post-processing: 0.784 -> 0.650 ms (3 / 4 / 5 / 6 CTAs: 0.659 / 0.657 / 0.650 / 0.671).
+#ifndef RN_SCAN_CTAS
+#define RN_SCAN_CTAS 5
+#endif
 template <int V, int L, int NV, int R>
-__global__ void __launch_bounds__(RN_THREADS)
+__global__ void __launch_bounds__(RN_THREADS, RN_SCAN_CTAS)
 rn_post_scan_kernel(const float *__restrict__ clas, const float *__restrict__ reg, int C,
                     const __grid_constant__ RnGeom g, const float4 *__restrict__ table,
                     const __grid_constant__ RnDecode dec, float thresh, int pack,
@@ -234,6 +241,12 @@ struct RnScanLvParams {
 };
 
 #define RN_SCANLV_THREADS 256
+// resident CTAs per SM the level-tensor scan is compiled for (as RN_SCAN_CTAS: ptxas needs the register budget to schedule the
+// loads early): unconstrained 70-80 registers 0.659-0.665 / 0.671-0.678 ms (probabilities / logits, COCO B=64), 3 CTAs 0.659 /
+// 0.650, 4 CTAs 0.644 / 0.650, 5 CTAs 0.646 / 0.656
+#ifndef RN_SCANLV_CTAS
+#define RN_SCANLV_CTAS 4
+#endif
 #define RN_SCANLV_U 8  // class planes in flight per thread
 
 // accurate sigmoid, the operations of torch's CUDA kernel (expf + IEEE divide): the scores equal those of
@@ -356,7 +369,7 @@ __device__ __forceinline__ void rn_scan_lv_body(const RnScanLvParams &S, const R
 }
 
 template <bool LOGITS>
-__global__ void __launch_bounds__(RN_SCANLV_THREADS)
+__global__ void __launch_bounds__(RN_SCANLV_THREADS, RN_SCANLV_CTAS)
 rn_post_scan_levels_kernel(const __grid_constant__ RnScanLvParams S, const __grid_constant__ RnGeom g,
                            const __grid_constant__ RnDecode dec) {
     __shared__ unsigned long long s_keys[RN_SCANLV_THREADS * 4];
